@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""Benchmark of the VBQ rate-distortion quantization step (BASELINE.json metric: coordinates quantized / second).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU)
+
+A "step" is one pass of the hot path over one batch: the Kodak-shaped bls2017 latent batch of BASELINE.json
+configs[1] (24 images x 32x48 x 192 channels = 7,077,888 coordinates, learned factorized prior at reference init,
+max_bits_per_coord=10, single lambda=0.5), written out as sorted quantile index (int32) + code length (float32)
+per coordinate, plus the per-lambda rate/distortion totals.  With N>1 every rank processes its own batch of that
+shape (weak scaling, no data-path collective) and the totals are all-reduced over NCCL inside the timed region.
+
+`value` is device-resident throughput (CUDA events, max over ranks); `e2e` goes through the reference-facing
+ChannelwisePriorCDFQuantizer.compress_batch_channel_latents-level call with pinned HOST buffers (H2D and D2H
+inside the timed region); `--impl reference` times the CPU oracle port of the reference's TF-eager quantizer."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMAGES, H, W, C, N_BITS = 24, 32, 48, 192, 10
+ROWS = IMAGES * H * W
+COORDS = ROWS * C
+LAMB = 0.5
+BYTES_PER_COORD = 16          # read mu, sigma; write quantile index + code length
+L2_BYTES = 126 * 2 ** 20
+METRIC = "VBQ coordinates quantized per second"
+UNIT = "coords/s"
+WORKLOAD = "bls2017 Kodak-shaped latents: 24x32x48x192, learned prior (reference init), N=10, lambda=0.5"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.12)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        good = [r for r in self.rows if len(r) == 6 and r[0].isdigit()]
+        if not good:
+            return None
+        sm = sorted(int(r[0]) for r in good)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in good)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(good[0][1]), "reasons": reasons, "samples": len(good)}
+
+
+# --------------------------------------------------------------------------------------------------------
+# synthetic workload
+# --------------------------------------------------------------------------------------------------------
+def prior_parameters(seed=2, init_scale=10.0):
+    """Reference initialisation of BMSHJ2018Prior (learned_prior.py:30-58) in NumPy: constant softplus^-1
+    matrices, biases U(-.5,.5), zero factors.  Used by both arms so they quantize against the same prior."""
+    rng = np.random.default_rng(seed)
+    fdims = (1, 3, 3, 3, 1)
+    scale = init_scale ** (1 / 4)
+    mats, bs, fs = [], [], []
+    for i in range(4):
+        init = np.log(np.expm1(1 / scale / fdims[i + 1]))
+        mats.append(np.logaddexp(0.0, np.full((C, fdims[i + 1], fdims[i]), init, dtype=np.float32)).astype(np.float32))
+        bs.append(rng.uniform(-.5, .5, size=(C, fdims[i + 1], 1)).astype(np.float32))
+        if i < 3:
+            fs.append(np.zeros((C, fdims[i + 1], 1), dtype=np.float32))
+    return mats, bs, fs
+
+
+def make_prior_and_quantizer(device):
+    import vbq_b200
+    prior = vbq_b200.BMSHJ2018Prior(C, dims=(3, 3, 3), init_scale=10., device=device)
+    prior.set_transformed_parameters(*prior_parameters())
+    q = vbq_b200.ChannelwisePriorCDFQuantizer(C, N_BITS, device=device)
+    q.build_code_points(prior)
+    return prior, q
+
+
+def make_batch_cpu(table, seed, n_images):
+    """CPU-only generator for the reference arm: mu by linear interpolation of the tabulated quantile function at
+    u ~ U(0.001, 0.999) (same distribution as `make_batch`), logvar ~ N(-3, 1.5^2)."""
+    rng = np.random.default_rng(seed)
+    rows = n_images * H * W
+    srt = np.sort(table, axis=1)
+    xi_sorted = (np.arange(srt.shape[1]) + 1.0) / (srt.shape[1] + 1.0)
+    u = rng.uniform(0.001, 0.999, (rows, C))
+    mu = np.stack([np.interp(u[:, c], xi_sorted, srt[c]) for c in range(C)], axis=1).astype(np.float32)
+    logvar = rng.normal(-3.0, 1.5, (rows, C)).astype(np.float32)
+    return mu, (np.exp(logvar) ** np.float32(0.5)).astype(np.float32)
+
+
+def make_batch(prior, seed, device):
+    """mu = F_c^-1(U(0.001,0.999)), logvar ~ N(-3, 1.5^2); returns (mu, sigma) (ROWS, C) f32."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    u = torch.rand((ROWS, C), generator=g, device=device, dtype=torch.float64) * 0.998 + 0.001
+    mu = prior.inverse_cdf(u).contiguous()
+    logvar = torch.randn((ROWS, C), generator=g, device=device, dtype=torch.float32) * 1.5 - 3.0
+    sigma = torch.exp(logvar) ** 0.5
+    return mu, sigma.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------------
+# CPU arm: oracle port of the reference's TF-eager quantizer (quantizer.py:156-188 + utils.py:363-423)
+# --------------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_init(table):
+    from oracle import vbq_oracle as O
+    oq = O.QuantizerNP(C, N_BITS)
+    oq.set_code_points(table, build_grids=True)
+    _W["q"] = oq
+
+
+def _cpu_one_image(args):
+    mu, sigma = args
+    Z, B = _W["q"].compress_batch_channel_latents(mu, sigma, [LAMB], fast_intervals=False)
+    return float(B[LAMB].sum())
+
+
+def cpu_throughput(table, mu, sigma, n_images, workers, repeats=1):
+    """coords/s of the oracle port over ``n_images`` Kodak-shaped images, one image per call like the reference's
+    evaluation loop (utils.py:535-542), ``workers`` processes."""
+    import multiprocessing as mp
+    per = H * W
+    jobs = [(mu[i * per:(i + 1) * per], sigma[i * per:(i + 1) * per]) for i in range(n_images)]
+    if workers <= 1:
+        _cpu_init(table)
+        t0 = time.perf_counter()
+        for _ in range(repeats):
+            for j in jobs:
+                _cpu_one_image(j)
+        dt = (time.perf_counter() - t0) / repeats
+    else:
+        with mp.get_context("fork").Pool(workers, initializer=_cpu_init, initargs=(table,)) as pool:
+            pool.map(_cpu_one_image, jobs[:workers])           # warm the workers
+            t0 = time.perf_counter()
+            for _ in range(repeats):
+                pool.map(_cpu_one_image, jobs, chunksize=1)
+            dt = (time.perf_counter() - t0) / repeats
+    return n_images * per * C / dt, dt
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference's CPU path (oracle port; TensorFlow 1.15 is not installable here) on the
+    host cores, rank 0 only."""
+    if rank != 0:
+        return
+    from oracle import vbq_oracle as O
+    pr = O.LearnedPriorNP(*prior_parameters())
+    xi = O.xi_heap(N_BITS)
+    table = pr.inverse_cdf_f64(np.repeat(xi[:, None], C, axis=1), iters=64).T
+    mu, sigma = make_batch_cpu(table, 1000, IMAGES)
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, IMAGES))
+    for _ in range(args.warmup):
+        cpu_throughput(table, mu, sigma, min(IMAGES, workers), workers)
+    vals = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, _ = cpu_throughput(table, mu, sigma, IMAGES, workers)
+        vals.append(v)
+    total = time.perf_counter() - t0
+    value = IMAGES * H * W * C * args.steps / total
+    sample = "%d Kodak-shaped images per step, one image per call, %d worker processes" % (IMAGES, workers)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# --------------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import vbq_b200
+    from vbq_b200 import ops, sharding
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    prior, q = make_prior_and_quantizer(dev)
+    pen, length = q._length_tables([LAMB])
+
+    # rotating buffer sets so that no step finds its inputs in the 126 MB L2
+    set_bytes = COORDS * BYTES_PER_COORD
+    n_sets = max(3, -(-3 * L2_BYTES // set_bytes))
+    sets = []
+    for s in range(n_sets):
+        mu, sigma = make_batch(prior, 1000 + 17 * rank + s, dev)
+        sets.append(dict(mu=mu, sigma=sigma,
+                         qidx=torch.empty((1, ROWS, C), dtype=torch.int32, device=dev),
+                         bits=torch.empty((1, ROWS, C), dtype=torch.float32, device=dev)))
+    totals = torch.zeros((1, 4), dtype=torch.float64, device=dev)
+    ws = ops.quantize_workspace(1, dev)
+
+    def step(i):
+        b = sets[i % n_sets]
+        ops.quantize_into(b["mu"], b["sigma"], q.all_code_points, q._packed, pen, length, None, N_BITS,
+                          qidx=b["qidx"], bits=b["bits"], totals=totals, workspace=ws, flags=args.flags)
+        if world > 1:
+            sharding.all_reduce_totals(totals)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev[0].record()
+        for i in range(args.steps):
+            step(args.warmup + i)
+            ev[i + 1].record()
+        barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = COORDS * world * args.steps / (total_ms * 1e-3)
+
+    # end-to-end through the reference-facing call with HOST buffers (pinned), H2D + D2H inside the timed region
+    h_mu = [b["mu"].cpu().pin_memory() for b in sets[:2]]
+    h_sigma = [b["sigma"].cpu().pin_memory() for b in sets[:2]]
+    h_q = torch.empty((ROWS, C), dtype=torch.int32).pin_memory()
+    h_b = torch.empty((ROWS, C), dtype=torch.float32).pin_memory()
+    h_tot = torch.empty((1, 4), dtype=torch.float64).pin_memory()
+
+    def e2e_step(i):
+        b = sets[i % n_sets]
+        b["mu"].copy_(h_mu[i % 2], non_blocking=True)
+        b["sigma"].copy_(h_sigma[i % 2], non_blocking=True)
+        step(i)
+        h_q.copy_(b["qidx"][0], non_blocking=True)
+        h_b.copy_(b["bits"][0], non_blocking=True)
+        h_tot.copy_(totals, non_blocking=True)
+        torch.cuda.synchronize()
+        return float(h_tot[0, 1])
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = COORDS * world * e2e_steps / float(t.item())
+
+    if rank != 0:
+        return
+    peaks, peak_kind = measured_peaks()
+    kern_ms = float(np.median(per_launch_ms))
+    achieved = COORDS * BYTES_PER_COORD / (kern_ms * 1e-3) / 1e9
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        b = sets[0]
+        n_img = 8
+        v, dt = cpu_throughput(q.all_code_points.cpu().numpy(), b["mu"][:n_img * H * W].cpu().numpy(),
+                               b["sigma"][:n_img * H * W].cpu().numpy(), n_img, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "%d of the 24 Kodak-shaped images (%d coordinates), one image per call, %.1f s"
+                         % (n_img, n_img * H * W * C, dt)}
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "coords_per_step_per_gpu": COORDS, "max_bits_per_coord": N_BITS,
+                   "lambdas": [LAMB], "outputs": "sorted quantile index int32 + code length f32 + totals",
+                   "l2": "%d rotating input/output sets (%d MB) > 126 MB L2" % (n_sets, n_sets * set_bytes >> 20),
+                   "flags": args.flags, "parallelism": "dp%d, one all-reduce of (n_lambda,4) f64 totals" % world},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                     "kernel": "vbq_quantize_kernel", "kernel_ms": kern_ms,
+                     "algorithmic_bytes_per_launch": COORDS * BYTES_PER_COORD},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * COORDS * 4,
+                "d2h_bytes_per_step": 2 * COORDS * 4 + 32, "steps": e2e_steps},
+        "gpu_launches": args.steps,
+        "clocks": clocks.summary(),
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--flags", type=int, default=0, help="VBQ_FLAG_* bits passed to vbq_quantize")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

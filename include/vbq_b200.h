@@ -1,0 +1,121 @@
+/*
+ * vbq_b200 — C ABI of the B200-native VBQ rate-distortion quantization path.
+ *
+ * The reference (mandt-lab/vbq) has no FFI layer: its boundary is the Python surface of
+ * img-compression/quantizer.py, learned_prior.py, vae_models.py, utils.py and one notebook cell.  Each entry
+ * point below names the reference interface it replaces (paths relative to the reference root).  All pointers
+ * prefixed d_ are DEVICE pointers owned by the caller; the library never allocates, keeps no global state and
+ * orders all work on the given stream (a cudaStream_t passed as void*, NULL = legacy default stream).  Every
+ * function returns a VBQ_* status (0 = ok) and never throws; vbq_last_error() gives the thread's last message.
+ *
+ * Data layout
+ *   latents        (rows, C) float32, channel-last, row-major  — quantizer.py:196-197 reshape(-1, C)
+ *   code points    (C, Q) float32, Q = 2^(N+1)-1, HEAP order: entry h = 2^n-1+i is F_c^-1((i+1/2)2^-n)
+ *                  — quantizer.py:30-36 `all_code_points`; the notebook's `codepoints` (ipynb:383-390) is one row
+ *   packed table   ceil(C/16) groups x min(Q, 2047) entries x 16 channels, the shared-memory image of a
+ *                  16-channel group (levels 0..10); made by vbq_pack_code_points
+ *   prior params   (C, 43) float32: for layer k=0..3: matrix (d_{k+1} x d_k row-major), bias (d_{k+1}),
+ *                  factor (d_{k+1}, k<3), dims (1,3,3,3,1), already softplus/tanh-transformed
+ *                  — learned_prior.py:30-58 `_matrices`, `_biases`, `_factors`
+ *   penalties      (n_lambda, pen_channels, N+1) float32 = fl(float32(lambda) * float32(len[c][n])),
+ *                  pen_channels = 1 (raw lengths len = n, quantizer.py:166-169) or C (corrected lengths
+ *                  n + R_lambda[c][n], quantizer.py:170-180); utils.py:393-396 forms exactly this product
+ *   sorted index   q = (2i+1) 2^(N-n) - 1, the rank of code point (n,i) among the channel's Q ascending code
+ *                  points — what quantizer.py:135,223 compute by searchsorted(code_points_by_channel, z_hat)
+ */
+#ifndef VBQ_B200_H
+#define VBQ_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VBQ_VERSION 100
+
+enum {
+    VBQ_OK = 0,
+    VBQ_ERR_NULL_POINTER = 1,
+    VBQ_ERR_BAD_SHAPE = 2,     /* rows < 0, C < 1, n_lambda < 1, pen_channels not in {1, C} */
+    VBQ_ERR_BAD_DEPTH = 3,     /* N outside [0, VBQ_MAX_DEPTH] */
+    VBQ_ERR_BAD_FLAGS = 4,
+    VBQ_ERR_WORKSPACE = 5,     /* workspace missing or too small */
+    VBQ_ERR_CUDA = 6,          /* a CUDA runtime call failed; see vbq_last_error() */
+    VBQ_ERR_MISALIGNED = 7
+};
+
+#define VBQ_MAX_DEPTH 20
+#define VBQ_PRIOR_PARAMS 43
+#define VBQ_GROUP 16             /* channels interleaved per shared-memory group */
+#define VBQ_SMEM_LEVELS 11       /* bit depths 0..10 of a group live in shared memory */
+#define VBQ_TOTALS 4             /* per lambda: sum raw depth n, sum code length, sum entropy-model bits, sum (z_hat-mu)^2/(2 sigma^2) */
+
+/* flags of vbq_quantize */
+#define VBQ_FLAG_LOGVAR   1u     /* d_sigma holds log-variances; sigma = sqrt(exp(logvar)) (quantizer.py:193-198) */
+#define VBQ_FLAG_NO_PRUNE 2u     /* visit every bit depth even when deeper levels provably cannot win */
+#define VBQ_FLAG_FAST     4u     /* score with d*d*(0.5/sigma^2) + pen on the nearer bracket end only (not bit-faithful
+                                    to utils.py:318-320 rounding; differs only inside float32 rounding ties) */
+
+int vbq_version(void);
+const char *vbq_status_string(int status);
+const char *vbq_last_error(void);
+
+/* ---- prior models -------------------------------------------------------------------------------------- */
+
+/* BMSHJ2018Prior.cdf (learned_prior.py:109-148): d_x, d_cdf (rows, C) float32 channel-last. */
+int vbq_learned_cdf(const float *d_params, int C, const float *d_x, long long rows, float *d_cdf, void *stream);
+
+/* BMSHJ2018Prior.inverse_cdf (learned_prior.py:173-218): d_xi (rows, C) float64 in (0,1) -> d_z (rows, C)
+ * float32.  Solves logits_c(z) = logit(xi) in float64 by bracketed Newton and rounds to float32, so the
+ * result is a pure function of (channel parameters, xi). */
+int vbq_learned_inverse_cdf(const float *d_params, int C, const double *d_xi, long long rows, float *d_z,
+                            void *stream);
+
+/* StandardGaussianPrior / FactoredGaussianPrior.inverse_cdf (vae_models.py:23-25, :40-43) and the notebook's
+ * norm.ppf(xi, scale=empirical_std) (ipynb:385): d_z = mean[c] + std[c] * ndtri(xi), float64.
+ * d_mean / d_std may be NULL (0 / 1). */
+int vbq_gaussian_inverse_cdf(const double *d_mean, const double *d_std, int C, const double *d_xi,
+                             long long rows, double *d_z, void *stream);
+
+/* ---- code-point tables (ChannelwisePriorCDFQuantizer.build_code_points, quantizer.py:25-63) ------------ */
+
+int vbq_build_code_points_learned(const float *d_params, int C, int N, float *d_table, void *stream);
+int vbq_build_code_points_gaussian(const double *d_mean, const double *d_std, int C, int N, float *d_table,
+                                   void *stream);
+long long vbq_packed_table_floats(int C, int N);
+int vbq_pack_code_points(const float *d_table, int C, int N, float *d_packed, void *stream);
+
+/* ---- the hot path -------------------------------------------------------------------------------------- */
+
+long long vbq_quantize_workspace_bytes(int n_lambda);
+
+/* Replaces ChannelwisePriorCDFQuantizer.get_all_N_bit_intervals + compress_batch_channel_latents
+ * (quantizer.py:65-80, :156-188), utils.curry_normal_logpdf + utils.batch_quantize_indep_dims
+ * (utils.py:307-327, :363-423) and the sorted-index / entropy-model gather of compress_latents
+ * (quantizer.py:223-228) for n_lambda rate-distortion trade-offs at once.  For every coordinate it finds the
+ * bracketing code points of mu at each bit depth and returns the first maximiser (candidate order left_0..left_N,
+ * right_1..right_N) of  -0.5*((z-mu)/sigma)^2 - penalty[lambda][c][n]  in float32 arithmetic.
+ *
+ * Outputs (any may be NULL), each (n_lambda, rows, C):
+ *   d_zhat      float32  chosen code point                       (Z_hat_dict[lamb])
+ *   d_qidx      int32    its sorted quantile index               (I / qidx, quantizer.py:135,223)
+ *   d_level     int32    its bit depth n                         (raw_num_bits in raw-length mode)
+ *   d_bits      float32  d_length[lambda][c][n] (n if d_length is NULL)  (num_bits_dict[lamb])
+ *   d_em_bits   float32  d_entropy_model[lambda][c][q]           (num_bits, quantizer.py:226-228)
+ * d_totals (n_lambda, VBQ_TOTALS) float64 receives the per-lambda sums (deterministic reduction order).
+ * d_length has the shape of d_penalty; d_entropy_model is (n_lambda, C, Q) float32. */
+int vbq_quantize(const float *d_mu, const float *d_sigma, long long rows, int C,
+                 const float *d_table, const float *d_packed, int N,
+                 const float *d_penalty, const float *d_length, int n_lambda, int pen_channels,
+                 const float *d_entropy_model,
+                 float *d_zhat, int *d_qidx, int *d_level, float *d_bits, float *d_em_bits,
+                 double *d_totals, void *d_workspace, long long workspace_bytes,
+                 unsigned flags, void *stream);
+
+/* Self-test helper: out[i] = the kernel's division a[i]/b[i] (reciprocal + FMA correction) so that tests can
+ * compare it with IEEE division bit for bit. */
+int vbq_selftest_divide(const float *d_a, const float *d_b, long long n, float *d_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VBQ_B200_H */

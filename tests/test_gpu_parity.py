@@ -1,0 +1,161 @@
+"""GPU parity tests: the CUDA path (through the C ABI / custom ops) against the CPU oracle.
+
+Protocol: (A) kernel code-point table vs oracle table; (B) oracle search run on the
+kernel-exported table must match the kernel's z_hat / code length bit for bit; (C) totals; float tolerances are
+written next to each assertion."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vbq_oracle as O
+import vbq_test_helpers as H
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _dev(x, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(x))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(DEV)
+
+
+def test_division_is_ieee():
+    import vbq_b200
+    rng = np.random.default_rng(0)
+    n = 1 << 22
+    a = (rng.standard_normal(n) * np.exp(rng.uniform(-20, 20, n))).astype(np.float32)
+    b = np.exp(rng.uniform(-20, 20, n)).astype(np.float32) * rng.choice([-1, 1], n).astype(np.float32)
+    out = vbq_b200.ops.selftest_divide(_dev(a), _dev(b)).cpu().numpy()
+    assert np.array_equal(out, a / b)
+
+
+@pytest.mark.parametrize("N,C,fs", [(10, 24, 0.5), (10, 16, 0.0), (12, 5, 0.5)])
+def test_learned_table_matches_f64_oracle(N, C, fs):
+    import vbq_b200
+    pr = H.make_prior(C, seed=11, factor_std=fs)
+    params = _dev(pr.packed())
+    table = vbq_b200.ops.build_code_points_learned(params, N).cpu().numpy()
+    xi = O.xi_heap(N)
+    want = pr.inverse_cdf_f64(np.repeat(xi[:, None], C, axis=1)).T
+    # correctly rounded float64 root on both sides: at most one float32 ulp apart, almost always identical
+    ulp = np.abs(table.view(np.int32).astype(np.int64) - want.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 1
+    assert (ulp == 0).mean() > 0.999
+    # strictly increasing in sorted order => heap order is a binary search tree
+    n = np.repeat(np.arange(N + 1), [2 ** k for k in range(N + 1)])
+    i = np.concatenate([np.arange(2 ** k) for k in range(N + 1)])
+    order = np.argsort(O.heap_to_sorted_rank(n, i, N))
+    assert np.all(np.diff(table[:, order], axis=1) > 0)
+    # same device routine behind inverse_cdf: bit-identical
+    xi_rep = _dev(np.repeat(xi[:, None], C, axis=1))
+    z = vbq_b200.ops.learned_inverse_cdf(params, xi_rep).cpu().numpy()
+    assert np.array_equal(z.T, table)
+    # reference-faithful float32 bisection (learned_prior.py:173-218): 1e-5 of the prior's scale
+    ref = pr.inverse_cdf_reference(np.repeat(xi[:, None], C, axis=1)).T
+    scale = np.abs(want).max()
+    assert np.max(np.abs(ref - table) / np.maximum(np.abs(want), 0.05 * scale)) < 1e-4
+
+
+def test_learned_cdf_matches_oracle():
+    import vbq_b200
+    C = 20
+    pr = H.make_prior(C, seed=3)
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal((1000, C)) * 30).astype(np.float32)
+    got = vbq_b200.ops.learned_cdf(_dev(pr.packed()), _dev(x)).cpu().numpy()
+    want = pr.cdf(x.astype(np.float64), dtype=np.float64)
+    assert np.max(np.abs(got - want)) < 2e-6   # float32 evaluation of a CDF in [0,1]
+
+
+def test_gaussian_tables_match_scipy():
+    import vbq_b200
+    N, C = 10, 7
+    rng = np.random.default_rng(5)
+    mean, std = rng.normal(0, 2, C), np.exp(rng.normal(0, 1, C))
+    table = vbq_b200.ops.build_code_points_gaussian(_dev(mean), _dev(std), N).cpu().numpy()
+    xi = O.xi_heap(N)
+    want64 = O.gaussian_inverse_cdf(np.repeat(xi[:, None], C, axis=1), mean, std)
+    z64 = vbq_b200.ops.gaussian_inverse_cdf(_dev(np.repeat(xi[:, None], C, axis=1)), _dev(mean), _dev(std)).cpu().numpy()
+    assert np.max(np.abs(z64 - want64) / np.maximum(np.abs(want64), 1e-3)) < 1e-13
+    ulp = np.abs(table.view(np.int32).astype(np.int64) - want64.astype(np.float32).T.view(np.int32).astype(np.int64))
+    assert ulp.max() <= 1 and (ulp == 0).mean() > 0.999
+
+
+def _run_case(N, C, rows, lambs, seed, corrected=False, flags=0, fs=0.5):
+    import vbq_b200
+    from vbq_b200 import ops
+    pr = H.make_prior(C, seed=seed, factor_std=fs)
+    table_d = ops.build_code_points_learned(_dev(pr.packed()), N)
+    table = table_d.cpu().numpy()
+    mu, sigma, _ = H.make_latents(pr, rows, seed + 1, table=table)
+    q = vbq_b200.ChannelwisePriorCDFQuantizer(C, N)
+    q.set_code_points(table_d)
+    oq = O.QuantizerNP(C, N)
+    oq.set_code_points(table, build_grids=(N <= 10))
+    if corrected:
+        rng = np.random.default_rng(seed + 2)
+        rcl = {l: (rng.uniform(0.5, 6.0, (C, N + 1))).astype(np.float32) for l in lambs}
+        q.raw_code_length_entropy_models = rcl
+        oq.raw_code_length_entropy_models = rcl
+    out = q.quantize(_dev(mu), _dev(sigma), lambs, flags=flags,
+                     outputs=ops.OUT_ZHAT | ops.OUT_QIDX | ops.OUT_LEVEL | ops.OUT_BITS | ops.OUT_TOTALS)
+    Zo, Bo, det = oq.compress_batch_channel_latents(mu, sigma, lambs, details=True)
+    res = []
+    for i, l in enumerate(lambs):
+        zk = out["zhat"][i].cpu().numpy()
+        bk = out["bits"][i].cpu().numpy()
+        lk = out["level"][i].cpu().numpy()
+        qk = out["qidx"][i].cpu().numpy()
+        res.append(dict(lamb=l, zk=zk, bk=bk, lk=lk, qk=qk, zo=Zo[l], bo=Bo[l], det=det[l],
+                        totals=out["totals"][i].cpu().numpy(), mu=mu, sigma=sigma, oq=oq))
+    return res
+
+
+@pytest.mark.parametrize("N,C,rows", [(10, 24, 1000), (10, 16, 64), (10, 5, 333), (4, 33, 257), (1, 3, 40),
+                                      (0, 2, 40), (12, 20, 500), (13, 16, 300)])
+@pytest.mark.parametrize("flags", [0, 2])
+def test_index_parity_raw_lengths(N, C, rows, flags):
+    lambs = [2.0 ** -8, 2.0 ** -3, 0.5, 2.0, 128.0]
+    for r in _run_case(N, C, rows, lambs, seed=100 + N, flags=flags):
+        # (B) bit-exact z_hat and depth against the oracle search on the kernel's own table
+        assert np.array_equal(r["zk"], r["zo"]), "lambda=%g" % r["lamb"]
+        assert np.array_equal(r["lk"], r["bo"])
+        assert np.array_equal(r["bk"], r["bo"].astype(np.float32))
+        # sorted index == searchsorted(code_points_by_channel, z_hat)  (quantizer.py:135) and the invariant :136-137
+        I = r["oq"].sorted_index(r["zk"])
+        assert np.array_equal(r["qk"], I)
+        assert np.array_equal(np.take_along_axis(r["oq"].code_points_by_channel.T, I, axis=0), r["zk"])
+        # (C) totals: float64 sums of float32 terms, 1e-9 relative
+        bits, dist = O.rd_totals(r["mu"], r["sigma"], r["zk"], r["bo"])
+        assert r["totals"][0] == bits and r["totals"][1] == bits
+        assert abs(r["totals"][3] - dist) <= 1e-6 * max(dist, 1.0)
+
+
+@pytest.mark.parametrize("N,C,rows", [(10, 24, 700), (6, 17, 300)])
+def test_index_parity_corrected_lengths(N, C, rows):
+    lambs = [2.0 ** -6, 0.5, 8.0]
+    for r in _run_case(N, C, rows, lambs, seed=7, corrected=True):
+        assert np.array_equal(r["zk"], r["zo"])
+        assert np.array_equal(r["bk"], r["bo"])
+
+
+def test_fast_mode_differs_only_inside_ties():
+    lambs = [2.0 ** -8, 0.5, 8.0]
+    tot = out = 0
+    for r in _run_case(10, 32, 4000, lambs, seed=21, flags=4):
+        n_mis, n_out = H.classify_mismatches(r["det"], r["zk"], r["bk"])
+        tot += n_mis
+        out += n_out
+    print("fast mode: %d mismatches, %d outside the 1e-6 tie band" % (tot, out))
+    assert out == 0
+
+
+def test_prune_equals_no_prune_large():
+    a = _run_case(10, 48, 6000, [2.0 ** -8, 0.5, 32.0], seed=33, flags=0)
+    b = _run_case(10, 48, 6000, [2.0 ** -8, 0.5, 32.0], seed=33, flags=2)
+    for x, y in zip(a, b):
+        assert np.array_equal(x["zk"], y["zk"]) and np.array_equal(x["lk"], y["lk"])
+        assert np.array_equal(x["zk"], x["zo"])

@@ -1,0 +1,16 @@
+"""vbq_b200 — B200-native implementation of VBQ's per-coordinate rate-distortion quantization path
+(reference: mandt-lab/vbq, img-compression/quantizer.py and the word-embedding notebook).
+
+Importing the package loads libvbq_b200.so; if it has not been built this raises (no CPU fallback)."""
+from . import _lib
+
+_lib.load()
+
+from . import ops, utils, sharding                                   # noqa: E402
+from .quantizer import ChannelwisePriorCDFQuantizer                  # noqa: E402
+from .learned_prior import BMSHJ2018Prior                            # noqa: E402
+from .vae_models import StandardGaussianPrior, FactoredGaussianPrior, GaussianVAE   # noqa: E402
+from .word_embeddings import GaussianCodebook                        # noqa: E402
+
+__all__ = ["ops", "utils", "sharding", "ChannelwisePriorCDFQuantizer", "BMSHJ2018Prior",
+           "StandardGaussianPrior", "FactoredGaussianPrior", "GaussianVAE", "GaussianCodebook"]

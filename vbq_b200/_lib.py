@@ -1,0 +1,76 @@
+"""ctypes binding of the C ABI declared in include/vbq_b200.h.
+
+There is no CPU fallback: if libvbq_b200.so is missing or a call fails, this module raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libvbq_b200.so")
+
+OK = 0
+FLAG_LOGVAR = 1
+FLAG_NO_PRUNE = 2
+FLAG_FAST = 4
+GROUP = 16
+TOTALS = 4
+PRIOR_PARAMS = 43
+MAX_DEPTH = 20
+
+
+class VbqError(RuntimeError):
+    def __init__(self, status, what, detail):
+        super().__init__("vbq_b200: %s (status %d): %s" % (what, status, detail))
+        self.status = status
+
+
+_p = C.c_void_p
+_ll = C.c_longlong
+_i = C.c_int
+_u = C.c_uint
+
+# name -> (restype, argtypes); must list every symbol of include/vbq_b200.h (tests/test_abi.py checks this)
+SIGNATURES = {
+    "vbq_version": (_i, []),
+    "vbq_status_string": (C.c_char_p, [_i]),
+    "vbq_last_error": (C.c_char_p, []),
+    "vbq_learned_cdf": (_i, [_p, _i, _p, _ll, _p, _p]),
+    "vbq_learned_inverse_cdf": (_i, [_p, _i, _p, _ll, _p, _p]),
+    "vbq_gaussian_inverse_cdf": (_i, [_p, _p, _i, _p, _ll, _p, _p]),
+    "vbq_build_code_points_learned": (_i, [_p, _i, _i, _p, _p]),
+    "vbq_build_code_points_gaussian": (_i, [_p, _p, _i, _i, _p, _p]),
+    "vbq_packed_table_floats": (_ll, [_i, _i]),
+    "vbq_pack_code_points": (_i, [_p, _i, _i, _p, _p]),
+    "vbq_quantize_workspace_bytes": (_ll, [_i]),
+    "vbq_quantize": (_i, [_p, _p, _ll, _i, _p, _p, _i, _p, _p, _i, _i, _p,
+                          _p, _p, _p, _p, _p, _p, _p, _ll, _u, _p]),
+    "vbq_selftest_divide": (_i, [_p, _p, _ll, _p, _p]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libvbq_b200.so (once).  Raises ImportError with build instructions when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "vbq_b200: %s not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `python -m vbq_b200.build`. There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != OK:
+        lib = load()
+        raise VbqError(status, what, "%s: %s" % (lib.vbq_status_string(status).decode(),
+                                                  lib.vbq_last_error().decode()))

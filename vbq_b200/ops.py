@@ -1,0 +1,278 @@
+"""PyTorch custom ops (`torch.library`) over the C ABI of libvbq_b200.so.
+
+PyTorch supplies device memory, the current stream and tracing metadata; all arithmetic happens in the
+hand-written sm_100a kernels.  Every op raises if the library is missing or the tensors are not CUDA tensors:
+there is deliberately no CPU implementation (north_star: "no CPU fallback")."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+from . import _lib
+
+OUT_ZHAT = 1
+OUT_QIDX = 2
+OUT_LEVEL = 4
+OUT_BITS = 8
+OUT_EM_BITS = 16
+OUT_TOTALS = 32
+
+FLAG_LOGVAR = _lib.FLAG_LOGVAR
+FLAG_NO_PRUNE = _lib.FLAG_NO_PRUNE
+FLAG_FAST = _lib.FLAG_FAST
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None or t.numel() == 0 else t.data_ptr()
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _need_cuda(name, t, dtype, ndim=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError("vbq_b200: `%s` must be a CUDA tensor (no CPU fallback exists)" % name)
+    if t.dtype != dtype:
+        raise TypeError("vbq_b200: `%s` must be %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("vbq_b200: `%s` must be contiguous" % name)
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError("vbq_b200: `%s` must be %d-D, got shape %s" % (name, ndim, tuple(t.shape)))
+
+
+def num_levels(max_bits: int) -> int:
+    return 2 ** (max_bits + 1) - 1
+
+
+# ------------------------------------------------------------------------------------------------------
+# raw call with caller-owned outputs (used by the op below and by the benchmark's preallocated plan)
+# ------------------------------------------------------------------------------------------------------
+def quantize_into(mu, sigma, table, packed, penalty, length, entropy_model, max_bits,
+                  zhat=None, qidx=None, level=None, bits=None, em_bits=None, totals=None,
+                  workspace=None, flags=0):
+    """Direct vbq_quantize call.  Outputs are (n_lambda, rows, C) tensors or None; see include/vbq_b200.h."""
+    lib = _lib.load()
+    _need_cuda("mu", mu, torch.float32, 2)
+    _need_cuda("sigma", sigma, torch.float32, 2)
+    _need_cuda("table", table, torch.float32, 2)
+    _need_cuda("packed", packed, torch.float32)
+    _need_cuda("penalty", penalty, torch.float32, 3)
+    if mu.shape != sigma.shape:
+        raise ValueError("vbq_b200: mu %s and sigma %s differ in shape" % (tuple(mu.shape), tuple(sigma.shape)))
+    rows, C = mu.shape
+    Q = num_levels(max_bits)
+    if tuple(table.shape) != (C, Q):
+        raise ValueError("vbq_b200: table must be (C=%d, Q=%d), got %s" % (C, Q, tuple(table.shape)))
+    n_lambda, pen_channels, n1 = penalty.shape
+    if n1 != max_bits + 1 or pen_channels not in (1, C):
+        raise ValueError("vbq_b200: penalty must be (n_lambda, 1 or C, N+1), got %s" % (tuple(penalty.shape),))
+    if packed.numel() != lib.vbq_packed_table_floats(C, max_bits):
+        raise ValueError("vbq_b200: packed table has the wrong size")
+    if length is not None:
+        _need_cuda("length", length, torch.float32, 3)
+        if length.shape != penalty.shape:
+            raise ValueError("vbq_b200: length must have the shape of penalty")
+    if entropy_model is not None:
+        _need_cuda("entropy_model", entropy_model, torch.float32, 3)
+        if tuple(entropy_model.shape) != (n_lambda, C, Q):
+            raise ValueError("vbq_b200: entropy_model must be (n_lambda, C, Q)")
+    for name, t, dt in (("zhat", zhat, torch.float32), ("qidx", qidx, torch.int32), ("level", level, torch.int32),
+                        ("bits", bits, torch.float32), ("em_bits", em_bits, torch.float32)):
+        if t is not None:
+            _need_cuda(name, t, dt)
+            if tuple(t.shape) != (n_lambda, rows, C):
+                raise ValueError("vbq_b200: `%s` must be (n_lambda, rows, C)" % name)
+    ws_bytes = 0
+    if totals is not None:
+        _need_cuda("totals", totals, torch.float64)
+        if tuple(totals.shape) != (n_lambda, _lib.TOTALS):
+            raise ValueError("vbq_b200: totals must be (n_lambda, %d)" % _lib.TOTALS)
+        if workspace is None:
+            raise ValueError("vbq_b200: totals need a workspace (see quantize_workspace)")
+        ws_bytes = workspace.numel() * workspace.element_size()
+    st = lib.vbq_quantize(_ptr(mu), _ptr(sigma), rows, C, _ptr(table), _ptr(packed), max_bits,
+                          _ptr(penalty), _ptr(length), n_lambda, pen_channels, _ptr(entropy_model),
+                          _ptr(zhat), _ptr(qidx), _ptr(level), _ptr(bits), _ptr(em_bits), _ptr(totals),
+                          _ptr(workspace), ws_bytes, flags, _stream(mu.device))
+    _lib.check(st, "vbq_quantize")
+
+
+def quantize_workspace(n_lambda, device):
+    n = _lib.load().vbq_quantize_workspace_bytes(n_lambda)
+    return torch.empty((n + 7) // 8, dtype=torch.float64, device=device)
+
+
+# ------------------------------------------------------------------------------------------------------
+# torch.library custom ops
+# ------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("vbq::quantize", mutates_args=())
+def quantize(mu: torch.Tensor, sigma: torch.Tensor, table: torch.Tensor, packed: torch.Tensor,
+             penalty: torch.Tensor, length: Optional[torch.Tensor], entropy_model: Optional[torch.Tensor],
+             max_bits: int, outputs: int, flags: int) -> List[torch.Tensor]:
+    """Rate-distortion search for every coordinate and every lambda.
+
+    Returns [zhat f32, qidx i32, level i32, bits f32, em_bits f32, totals f64]; entries whose OUT_* bit is not
+    set in ``outputs`` are empty tensors."""
+    rows, C = mu.shape
+    L = penalty.shape[0]
+    dev = mu.device
+
+    def alloc(bit, dtype):
+        return torch.empty((L, rows, C), dtype=dtype, device=dev) if outputs & bit else None
+
+    zhat = alloc(OUT_ZHAT, torch.float32)
+    qidx = alloc(OUT_QIDX, torch.int32)
+    level = alloc(OUT_LEVEL, torch.int32)
+    bits = alloc(OUT_BITS, torch.float32)
+    em_bits = alloc(OUT_EM_BITS, torch.float32)
+    totals = ws = None
+    if outputs & OUT_TOTALS:
+        totals = torch.empty((L, _lib.TOTALS), dtype=torch.float64, device=dev)
+        ws = quantize_workspace(L, dev)
+    quantize_into(mu, sigma, table, packed, penalty, length, entropy_model, max_bits,
+                  zhat, qidx, level, bits, em_bits, totals, ws, flags)
+    empty = lambda dt: torch.empty(0, dtype=dt, device=dev)  # noqa: E731
+    return [zhat if zhat is not None else empty(torch.float32),
+            qidx if qidx is not None else empty(torch.int32),
+            level if level is not None else empty(torch.int32),
+            bits if bits is not None else empty(torch.float32),
+            em_bits if em_bits is not None else empty(torch.float32),
+            totals if totals is not None else empty(torch.float64)]
+
+
+@quantize.register_fake
+def _(mu, sigma, table, packed, penalty, length, entropy_model, max_bits, outputs, flags):
+    rows, C = mu.shape
+    L = penalty.shape[0]
+
+    def shp(bit):
+        return (L, rows, C) if outputs & bit else (0,)
+
+    return [mu.new_empty(shp(OUT_ZHAT)), mu.new_empty(shp(OUT_QIDX), dtype=torch.int32),
+            mu.new_empty(shp(OUT_LEVEL), dtype=torch.int32), mu.new_empty(shp(OUT_BITS)),
+            mu.new_empty(shp(OUT_EM_BITS)),
+            mu.new_empty((L, _lib.TOTALS) if outputs & OUT_TOTALS else (0,), dtype=torch.float64)]
+
+
+@torch.library.custom_op("vbq::learned_cdf", mutates_args=())
+def learned_cdf(params: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """BMSHJ2018Prior.cdf on (rows, C) channel-last float32 (learned_prior.py:109-148)."""
+    _need_cuda("params", params, torch.float32, 2)
+    _need_cuda("x", x, torch.float32, 2)
+    C = params.shape[0]
+    if params.shape[1] != _lib.PRIOR_PARAMS or x.shape[1] != C:
+        raise ValueError("vbq_b200: params must be (C, 43) and x (rows, C)")
+    out = torch.empty_like(x)
+    st = _lib.load().vbq_learned_cdf(_ptr(params), C, _ptr(x), x.shape[0], _ptr(out), _stream(x.device))
+    _lib.check(st, "vbq_learned_cdf")
+    return out
+
+
+@learned_cdf.register_fake
+def _(params, x):
+    return torch.empty_like(x)
+
+
+@torch.library.custom_op("vbq::learned_inverse_cdf", mutates_args=())
+def learned_inverse_cdf(params: torch.Tensor, xi: torch.Tensor) -> torch.Tensor:
+    """BMSHJ2018Prior.inverse_cdf: xi (rows, C) float64 -> float32 (learned_prior.py:173-218)."""
+    _need_cuda("params", params, torch.float32, 2)
+    _need_cuda("xi", xi, torch.float64, 2)
+    C = params.shape[0]
+    if params.shape[1] != _lib.PRIOR_PARAMS or xi.shape[1] != C:
+        raise ValueError("vbq_b200: params must be (C, 43) and xi (rows, C)")
+    out = torch.empty(xi.shape, dtype=torch.float32, device=xi.device)
+    st = _lib.load().vbq_learned_inverse_cdf(_ptr(params), C, _ptr(xi), xi.shape[0], _ptr(out), _stream(xi.device))
+    _lib.check(st, "vbq_learned_inverse_cdf")
+    return out
+
+
+@learned_inverse_cdf.register_fake
+def _(params, xi):
+    return xi.new_empty(xi.shape, dtype=torch.float32)
+
+
+@torch.library.custom_op("vbq::gaussian_inverse_cdf", mutates_args=())
+def gaussian_inverse_cdf(xi: torch.Tensor, mean: Optional[torch.Tensor], std: Optional[torch.Tensor]) -> torch.Tensor:
+    """norm.ppf(xi, loc=mean, scale=std) in float64; xi (rows, C) (vae_models.py:23-25,40-43; ipynb:385)."""
+    _need_cuda("xi", xi, torch.float64, 2)
+    C = xi.shape[1]
+    for name, t in (("mean", mean), ("std", std)):
+        if t is not None:
+            _need_cuda(name, t, torch.float64, 1)
+            if t.shape[0] != C:
+                raise ValueError("vbq_b200: `%s` must have C=%d entries" % (name, C))
+    out = torch.empty_like(xi)
+    st = _lib.load().vbq_gaussian_inverse_cdf(_ptr(mean), _ptr(std), C, _ptr(xi), xi.shape[0], _ptr(out),
+                                              _stream(xi.device))
+    _lib.check(st, "vbq_gaussian_inverse_cdf")
+    return out
+
+
+@gaussian_inverse_cdf.register_fake
+def _(xi, mean, std):
+    return torch.empty_like(xi)
+
+
+@torch.library.custom_op("vbq::build_code_points_learned", mutates_args=())
+def build_code_points_learned(params: torch.Tensor, max_bits: int) -> torch.Tensor:
+    """(C, Q) heap-order code-point table of a learned prior (quantizer.py:25-36)."""
+    _need_cuda("params", params, torch.float32, 2)
+    C = params.shape[0]
+    out = torch.empty((C, num_levels(max_bits)), dtype=torch.float32, device=params.device)
+    st = _lib.load().vbq_build_code_points_learned(_ptr(params), C, max_bits, _ptr(out), _stream(params.device))
+    _lib.check(st, "vbq_build_code_points_learned")
+    return out
+
+
+@build_code_points_learned.register_fake
+def _(params, max_bits):
+    return params.new_empty((params.shape[0], num_levels(max_bits)))
+
+
+@torch.library.custom_op("vbq::build_code_points_gaussian", mutates_args=())
+def build_code_points_gaussian(mean: torch.Tensor, std: torch.Tensor, max_bits: int) -> torch.Tensor:
+    """(C, Q) heap-order code-point table of per-channel Gaussians N(mean[c], std[c]^2)."""
+    _need_cuda("mean", mean, torch.float64, 1)
+    _need_cuda("std", std, torch.float64, 1)
+    C = mean.shape[0]
+    out = torch.empty((C, num_levels(max_bits)), dtype=torch.float32, device=mean.device)
+    st = _lib.load().vbq_build_code_points_gaussian(_ptr(mean), _ptr(std), C, max_bits, _ptr(out),
+                                                    _stream(mean.device))
+    _lib.check(st, "vbq_build_code_points_gaussian")
+    return out
+
+
+@build_code_points_gaussian.register_fake
+def _(mean, std, max_bits):
+    return mean.new_empty((mean.shape[0], num_levels(max_bits)), dtype=torch.float32)
+
+
+@torch.library.custom_op("vbq::pack_code_points", mutates_args=())
+def pack_code_points(table: torch.Tensor, max_bits: int) -> torch.Tensor:
+    """Shared-memory image of the table: (groups, min(Q, 2047), 16) (include/vbq_b200.h)."""
+    _need_cuda("table", table, torch.float32, 2)
+    C = table.shape[0]
+    lib = _lib.load()
+    out = torch.empty(lib.vbq_packed_table_floats(C, max_bits), dtype=torch.float32, device=table.device)
+    st = lib.vbq_pack_code_points(_ptr(table), C, max_bits, _ptr(out), _stream(table.device))
+    _lib.check(st, "vbq_pack_code_points")
+    return out
+
+
+@pack_code_points.register_fake
+def _(table, max_bits):
+    C = table.shape[0]
+    g = (C + _lib.GROUP - 1) // _lib.GROUP
+    return table.new_empty(g * min(num_levels(max_bits), 2047) * _lib.GROUP)
+
+
+def selftest_divide(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    _need_cuda("a", a, torch.float32)
+    _need_cuda("b", b, torch.float32)
+    out = torch.empty_like(a)
+    st = _lib.load().vbq_selftest_divide(_ptr(a), _ptr(b), a.numel(), _ptr(out), _stream(a.device))
+    _lib.check(st, "vbq_selftest_divide")
+    return out

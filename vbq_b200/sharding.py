@@ -1,0 +1,68 @@
+"""Batch/row sharding over the GPUs of one node.
+
+Every coordinate is independent given the (replicated, <= 55 KB) prior and the lambda list, so ranks take
+contiguous slices of the leading axis (images or embedding rows) and never exchange latents.  The only
+collective is one all-reduce(SUM) of the (n_lambda, 4) float64 rate/distortion totals; entropy-model fitting adds
+an int64 histogram all-reduce.  One process per GPU, `torch.distributed` (NCCL over NVLink on the B200 box, gloo in
+the CPU tests)."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_items, world_size, rank):
+    """Contiguous split of ``n_items`` leading-axis units: the first ``n_items % world_size`` ranks get one
+    extra.  Returns (start, stop)."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError("bad rank %d / world size %d" % (rank, world_size))
+    base, rem = divmod(int(n_items), world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_leading_axis(x, world_size=None, rank=None):
+    """This rank's contiguous slice of ``x`` along axis 0."""
+    world_size = dist.get_world_size() if world_size is None else world_size
+    rank = dist.get_rank() if rank is None else rank
+    a, b = shard_bounds(x.shape[0], world_size, rank)
+    return x[a:b]
+
+
+def all_reduce_totals(totals, group=None):
+    """Sum the per-shard (n_lambda, 4) float64 totals over all ranks, in place; returns ``totals``.
+    Columns: sum of raw depth n, sum of code length, sum of entropy-model bits, sum (z_hat-mu)^2/(2 sigma^2)."""
+    if totals.dtype != torch.float64:
+        raise TypeError("totals must be float64")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=group)
+    return totals
+
+
+def all_reduce_counts(counts, group=None):
+    """Sum int64 histogram counts over all ranks (entropy-model fitting, reference quantizer.py:104-105,138-140)."""
+    if counts.dtype != torch.int64:
+        raise TypeError("counts must be int64")
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return counts
+
+
+class ShardedQuantizer:
+    """Data-parallel wrapper: each rank quantizes its slice and the per-lambda totals are all-reduced."""
+
+    def __init__(self, quantizer, group=None):
+        self.quantizer = quantizer
+        self.group = group
+
+    def rd_sweep(self, local_means, local_scales, lambs, logvar=False, entropy_bits=False, flags=0):
+        """Totals-only rate-distortion sweep over this rank's shard; returns the global (n_lambda, 4) totals."""
+        from . import ops
+        out = self.quantizer.quantize(local_means, local_scales, lambs, logvar=logvar, outputs=ops.OUT_TOTALS,
+                                      flags=flags, entropy_bits=False)
+        return all_reduce_totals(out['totals'], self.group)
+
+    def build_entropy_models_from_latents(self, local_means, local_logvars, lambs, add_n_smoothing):
+        return self.quantizer.build_entropy_models_from_latents(
+            local_means, local_logvars, lambs, add_n_smoothing,
+            reduce_fn=lambda c: all_reduce_counts(c, self.group))

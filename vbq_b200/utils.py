@@ -1,0 +1,52 @@
+"""Host-side helpers with the names of the reference's img-compression/utils.py (hot-path subset)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+def n_bit_binary_floats(n):
+    """Level-n quantiles xi = (i + 1/2) 2^-n, i < 2^n  (reference utils.py:23-24)."""
+    return [i * 2 ** (-n) + 2 ** (-n - 1) for i in range(2 ** n)]
+
+
+def all_bin_floats(max_bits):
+    """All Q = 2^(N+1)-1 quantiles in heap order (reference quantizer.py:30)."""
+    return np.hstack([n_bit_binary_floats(n) for n in range(max_bits + 1)])
+
+
+def heap_to_sorted_index(level, index, max_bits):
+    """Sorted rank q = (2i+1) 2^(N-n) - 1 of heap entry (n, i) (reference quantizer.py:37,135)."""
+    return (2 * index + 1) * (1 << (max_bits - level)) - 1
+
+
+class NormalLogpdf:
+    """Callable returned by `curry_normal_logpdf` (reference utils.py:307-327): f(z) = -0.5*((z-loc)/scale)^2
+    (+ const).  It carries loc/scale so that `batch_quantize_indep_dims` can hand them to the CUDA kernel
+    instead of materialising f(P)."""
+
+    def __init__(self, loc, scale, ignore_const):
+        self.loc, self.scale, self.ignore_const = loc, scale, ignore_const
+
+    def __call__(self, z):
+        out = -0.5 * ((z - self.loc) / self.scale) ** 2
+        if not self.ignore_const:
+            out = out - torch.log(torch.as_tensor(self.scale)) - 0.5 * float(np.log(2 * np.pi))
+        return out
+
+
+def curry_normal_logpdf(loc, scale, ignore_const=False, backend=None):
+    """Reference utils.py:307-327.  ``backend`` is accepted for signature compatibility and ignored."""
+    return NormalLogpdf(loc, scale, ignore_const)
+
+
+def as_device_f32(x, device):
+    """numpy / torch (any device) -> contiguous float32 CUDA tensor."""
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.float32).contiguous()
+    return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).to(device)
+
+
+def lambda_key_list(lambs):
+    """The reference keys its dicts by the lambda objects themselves (quantizer.py:172,226)."""
+    return list(lambs)

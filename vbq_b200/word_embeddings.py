@@ -1,0 +1,85 @@
+"""Word-embedding VBQ: the notebook cells of the reference's
+word-embeddings/compress-trained-word-embeddings.ipynb:373-390 (code points) and :429-443
+(`compress_coordinates`), on the GPU.
+
+All coordinates share one zero-mean Gaussian prior N(0, empirical_std^2).  The shared code-point tree is
+replicated over 16 virtual channels so the same sm_100a kernel as the image path walks it
+(bank-conflict-free interleaving, include/vbq_b200.h)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+
+_VC = 16  # virtual channels = VBQ_GROUP
+
+
+def empirical_std(means):
+    """ipynb:373-374: sqrt(mean(mu^2))."""
+    m = means if isinstance(means, torch.Tensor) else torch.as_tensor(np.asarray(means))
+    return float(torch.sqrt(torch.mean(m.double().reshape(-1) ** 2)))
+
+
+class GaussianCodebook:
+    """`codepoints` / `lengths` of the notebook (heap order, float64 / int64) plus the device tables."""
+
+    def __init__(self, empirical_std, max_codepoint_length=10, device="cuda"):
+        self.max_codepoint_length = int(max_codepoint_length)
+        self.empirical_std = float(empirical_std)
+        self.device = torch.device(device)
+        N = self.max_codepoint_length
+        # codepoint_xi = np.arange(0.5**(length+1), 1, 0.5**length), length-major (ipynb:383-388)
+        xi = np.concatenate([np.arange(0.5 ** (n + 1), 1, 0.5 ** n) for n in range(N + 1)])
+        xi_d = torch.from_numpy(xi).to(self.device).reshape(-1, 1)
+        std_d = torch.tensor([self.empirical_std], dtype=torch.float64, device=self.device)
+        pts = ops.gaussian_inverse_cdf(xi_d, None, std_d).reshape(-1)          # norm.ppf(xi, scale=std), float64
+        self.codepoints = pts.cpu().numpy()
+        self.lengths = np.concatenate([np.full(2 ** n, n, dtype=np.int64) for n in range(N + 1)])
+        self._table = pts.to(torch.float32).reshape(1, -1).repeat(_VC, 1).contiguous()   # (16, Q)
+        self._packed = ops.pack_code_points(self._table, N)
+
+    def _level_lengths(self, bitlengths):
+        N = self.max_codepoint_length
+        bl = np.asarray(bitlengths)
+        per_level = np.array([bl[2 ** n - 1] for n in range(N + 1)], dtype=np.float64)
+        if not np.array_equal(np.repeat(per_level, [2 ** n for n in range(N + 1)]), bl.astype(np.float64)):
+            raise NotImplementedError("bitlengths must be constant within a bit depth for the bracketing search")
+        return per_level
+
+    def quantize(self, means, stds, betas, bitlengths=None, outputs=ops.OUT_ZHAT, flags=0):
+        """means, stds: float32 CUDA tensors of equal shape -> dict of (len(betas),) + means.shape tensors."""
+        N = self.max_codepoint_length
+        per_level = self._level_lengths(self.lengths if bitlengths is None else bitlengths).astype(np.float32)
+        pen = np.stack([np.float32(b) * per_level for b in betas])[:, None, :]
+        pen = torch.from_numpy(np.ascontiguousarray(pen, dtype=np.float32)).to(self.device)
+        length = torch.from_numpy(np.broadcast_to(per_level, (len(betas), 1, N + 1)).copy()).to(self.device)
+        m = means.reshape(-1)
+        s = stds.reshape(-1)
+        n = m.numel()
+        pad = (-n) % _VC
+        if pad:
+            m = torch.cat([m, m.new_zeros(pad)])
+            s = torch.cat([s, s.new_ones(pad)])
+        z, q, lv, b, _, tot = ops.quantize(m.reshape(-1, _VC).contiguous(), s.reshape(-1, _VC).contiguous(),
+                                           self._table, self._packed, pen, length, None, N, outputs, flags)
+        L = len(betas)
+
+        def unpad(t):
+            return t.reshape(L, -1)[:, :n].reshape((L,) + tuple(means.shape)) if t.numel() else t
+
+        return dict(zhat=unpad(z), qidx=unpad(q), level=unpad(lv), bits=unpad(b), totals=tot)
+
+    def compress_coordinates(self, means, stds, beta, bitlengths=None):
+        """Notebook signature (ipynb:429-443): returns (optima shaped and typed like `means`, None).
+        Minimises (c - mu)^2 + 2 beta sigma^2 len(c) over the code points, i.e. lambda = beta in
+        -0.5((c-mu)/sigma)^2 - lambda len."""
+        is_np = not isinstance(means, torch.Tensor)
+        m = torch.as_tensor(np.asarray(means)) if is_np else means
+        s = torch.as_tensor(np.asarray(stds)) if is_np else stds
+        m32 = m.to(device=self.device, dtype=torch.float32).contiguous()
+        s32 = s.to(device=self.device, dtype=torch.float32).contiguous()
+        out = self.quantize(m32, s32, [beta], bitlengths)['zhat'][0]
+        if is_np:
+            return out.cpu().numpy().astype(np.asarray(means).dtype), None
+        return out.to(means.dtype), None
