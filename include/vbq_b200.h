@@ -12,8 +12,9 @@
  *   latents        (rows, C) float32, channel-last, row-major  — quantizer.py:196-197 reshape(-1, C)
  *   code points    (C, Q) float32, Q = 2^(N+1)-1, HEAP order: entry h = 2^n-1+i is F_c^-1((i+1/2)2^-n)
  *                  — quantizer.py:30-36 `all_code_points`; the notebook's `codepoints` (ipynb:383-390) is one row
- *   packed table   ceil(C/16) groups x min(Q, 2047) entries x 16 channels, the shared-memory image of a
- *                  16-channel group (levels 0..10); made by vbq_pack_code_points
+ *   packed table   ceil(C/16) groups x 2069 entries x 16 channels, the shared-memory image of a 16-channel group:
+ *                  bit depths 0..10, each stored as [pad, 2^n points, pad] so bracket ends need no clamping;
+ *                  made by vbq_pack_code_points
  *   prior params   (C, 43) float32: for layer k=0..3: matrix (d_{k+1} x d_k row-major), bias (d_{k+1}),
  *                  factor (d_{k+1}, k<3), dims (1,3,3,3,1), already softplus/tanh-transformed
  *                  — learned_prior.py:30-58 `_matrices`, `_biases`, `_factors`

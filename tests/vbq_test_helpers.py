@@ -22,7 +22,7 @@ def make_latents(prior, rows, seed, edge_cases=True, table=None):
         if table is not None:  # exactly on code points of several depths, and one ulp around them
             Q = table.shape[1]
             for r, h in zip(range(3, 12), [0, 1, 2, 5, Q // 2, Q - 1, Q - 2, (Q - 1) // 2, 3]):
-                mu[r] = table[:, h]
+                mu[r] = table[:, h % Q]
             mu[12] = np.nextafter(table[:, Q - 1], np.float32(np.inf))
             mu[13] = np.nextafter(table[:, (Q - 1) // 2], np.float32(-np.inf))
             mu[14] = np.nextafter(table[:, 0], np.float32(np.inf))

@@ -1,0 +1,637 @@
+// quantize.cu — the rate-distortion search kernel (sm_100a) and its C ABI.
+//
+// Reference behaviour reproduced (paths relative to mandt-lab/vbq):
+//   img-compression/quantizer.py:65-80     per-depth bracket of mu (searchsorted in edge-padded grids)
+//   img-compression/quantizer.py:156-188   candidates left_0..left_N, right_1..right_N and their code lengths
+//   img-compression/utils.py:318-320       score -0.5*((z-mu)/sigma)^2, float32
+//   img-compression/utils.py:392-415       per lambda: score - lambda*len, first argmax, gather
+//   img-compression/quantizer.py:223-228   sorted index of z_hat and entropy-model bits
+//
+// Design.  The prior's quantile function tabulated on the dyadic grid is, in the reference's own heap order, an
+// implicit binary search tree (node (n,i) has children (n+1,2i), (n+1,2i+1)).  Walking it with one compare per bit
+// depth yields at every depth exactly the searchsorted bracket of the reference.  A CTA owns 16 channels: their
+// trees (depths 0..10, each level padded by one entry on both sides so that bracket ends never need clamping) sit
+// interleaved in shared memory (bank = channel + 16*(entry&1)); a warp covers 16 channels x 2 rows, so global
+// accesses are full 64-byte segments of the channel-last latents.  Each thread keeps its channel's penalties in
+// registers and processes U rows at a time for instruction-level parallelism, prefetching the next rows.  Only the
+// winning depth is tracked; the winning index is rebuilt from the final tree path.  No tensor cores: nothing here
+// is a dense contraction.
+#include <stdlib.h>
+
+#include "common.h"
+
+constexpr int kMaxThreads = 1024;
+constexpr int kSmemDepth = VBQ_SMEM_LEVELS - 1;                             // deepest level held in shared memory (10)
+constexpr int kPadEntries = (1 << VBQ_SMEM_LEVELS) - 1 + 2 * VBQ_SMEM_LEVELS;  // 2069 entries per channel
+constexpr int kMaxGrid = 1024;
+constexpr int kRowStrideBytes = VBQ_GROUP * 4;                              // 64 B between consecutive tree entries
+
+// padded entry index of code point (n, i): levels are stored as [pad, 2^n points, pad]
+__host__ __device__ constexpr int entry_of(int n, int i) { return (1 << n) + 2 * n + i; }
+
+struct QArgs {
+    const float *mu, *sigma;
+    long long rows;
+    int C;
+    const float *table, *packed;
+    int N, Q;
+    const float *pen, *len;
+    int n_lambda, pen_channels;
+    const float *em;
+    float *zhat;
+    int *qidx, *level;
+    float *bits, *em_bits;
+    double *totals, *partials;
+    unsigned *ticket;
+    unsigned flags;
+    int accumulate;        // add to d_totals instead of overwriting (row-chunked calls)
+    long long lam_stride;  // elements between the outputs of consecutive lambdas (total rows * C)
+    int n_groups;
+    long long passes, total_units;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// packed table: [group][entry][16 channels]; unused depths (> N) repeat the parent so the walk stays defined
+// ------------------------------------------------------------------------------------------------------------
+__global__ void pack_table_kernel(const float *__restrict__ table, int C, int N, int Q, int n_groups,
+                                  float *__restrict__ packed) {
+    const long long total = (long long)n_groups * kPadEntries * VBQ_GROUP;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int j = (int)(t % VBQ_GROUP);
+        const long long r = t / VBQ_GROUP;
+        const int e = (int)(r % kPadEntries);
+        const int g = (int)(r / kPadEntries);
+        const int c = min(g * VBQ_GROUP + j, C - 1);
+        // level of padded entry e: largest n with entry_of(n, -1) <= e
+        int n = 0;
+        while (n + 1 < VBQ_SMEM_LEVELS && entry_of(n + 1, -1) <= e) ++n;
+        const int k = e - entry_of(n, -1);          // 0 = left pad, 1..2^n = points, 2^n+1 = right pad
+        const int last = (1 << n) - 1;
+        int i = min(max(k - 1, 0), last);
+        // depth N has no edge padding in the reference (quantizer.py:57): above the highest point the bracket is
+        // (second highest, highest), so the right pad of depth N holds the second-highest point
+        if (n == N && k == last + 2) i = max(last - 1, 0);
+        int nn = n;
+        while (nn > N) {  // unused depth: repeat the ancestor at depth N
+            --nn;
+            i >>= 1;
+        }
+        packed[t] = table[(size_t)c * Q + ((1 << nn) - 1 + i)];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// scoring
+// ------------------------------------------------------------------------------------------------------------
+// a/b with a correctly rounded reciprocal r = RN(1/b): q0 = RN(a r), e = a - q0 b (exact in an FMA),
+// q = RN(q0 + e r) is the IEEE quotient (Markstein); checked bit for bit by tests/test_gpu_parity.py.
+__device__ __forceinline__ float div_rn(float a, float b, float r) {
+    const float q0 = __fmul_rn(a, r);
+    const float e = __fmaf_rn(-q0, b, a);
+    return __fmaf_rn(e, r, q0);
+}
+
+// utils.py:318-320 then :393-396:  fl( fl(-0.5 * fl(t*t)) - pen ),  t = fl(fl(z-mu)/sigma).
+// -0.5*t2 is exact, so one FMA reproduces the two roundings.  npen = -pen.
+__device__ __forceinline__ float score_exact(float z, float mu, float sg, float rs, float npen) {
+    const float t = div_rn(__fsub_rn(z, mu), sg, rs);
+    return __fmaf_rn(__fmul_rn(t, t), -0.5f, npen);
+}
+
+__device__ __forceinline__ float lds_f32(const char *base, int byte_off) {
+    return *reinterpret_cast<const float *>(base + byte_off);
+}
+
+// real index of padded position k (0..2^n+1) at depth n
+__device__ __forceinline__ int clamp_index(int first_ge, int n, int N, bool want_right) {
+    const int last = (1 << n) - 1;
+    if (want_right) return min(first_ge, last);
+    if (first_ge == 0) return 0;
+    if (first_ge > last) return n < N ? last : max(last - 1, 0);
+    return first_ge - 1;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// kernel
+// ------------------------------------------------------------------------------------------------------------
+// Packed two-coordinate scoring on Blackwell's f32x2 pipe (FADD2/FMUL2/FFMA2): the same IEEE roundings as the
+// scalar `score_exact`, two coordinates per instruction.  nmu = -mu, nsg = -sigma, rs = RN(1/sigma).
+__device__ __forceinline__ float2 score_exact2(float2 z, float2 nmu, float2 nsg, float2 rs, float2 npen) {
+    const float2 d = __fadd2_rn(z, nmu);
+    const float2 q0 = __fmul2_rn(d, rs);
+    const float2 e = __ffma2_rn(q0, nsg, d);
+    const float2 q = __ffma2_rn(e, rs, q0);
+    const float2 t2 = __fmul2_rn(q, q);
+    return __ffma2_rn(t2, make_float2(-0.5f, -0.5f), npen);
+}
+
+// FAST scoring: -(d*d)*w + npen on the nearer bracket end, w = 0.5/sigma^2
+__device__ __forceinline__ float2 score_fast2(float2 zp, float2 zn, float2 nmu, float2 nw, float2 npen) {
+    const float2 dp = __fadd2_rn(zp, nmu), dn = __fadd2_rn(zn, nmu);
+    const float2 d = make_float2(fminf(fabsf(dp.x), fabsf(dn.x)), fminf(fabsf(dp.y), fabsf(dn.y)));
+    return __ffma2_rn(__fmul2_rn(d, d), nw, npen);
+}
+
+// cp.async (LDGSTS) of one float into this thread's private staging slot: the next rows' mu / sigma travel
+// global -> shared asynchronously, kStages-1 iterations ahead, without holding registers or a scoreboard slot.
+__device__ __forceinline__ void cp_async_f32(float *smem_dst, const float *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N_) : "memory"); }
+
+constexpr int kStages = 4;   // staging ring depth (prefetch distance kStages-1 iterations)
+
+template <bool FAST, bool PRUNE, bool TOTALS, bool DEEP, int U, int kThreads>
+__global__ void __launch_bounds__(kThreads, 1) vbq_quantize_kernel(const QArgs a) {
+    static_assert(U % 2 == 0, "coordinates are processed in f32x2 pairs");
+    constexpr int RP = kThreads / VBQ_GROUP;              // rows covered by one pass of the CTA
+    constexpr int P = U / 2;                              // coordinate pairs per thread
+    extern __shared__ __align__(16) float smem[];
+    float *sT = smem;                                   // [kPadEntries][16] code points of depths 0..10
+    float *sPen = sT + kPadEntries * VBQ_GROUP;         // [N+1][16] negated penalties
+    float *sSuf = sPen + (a.N + 1) * VBQ_GROUP;         // [N+1][16] max over deeper levels of the negated penalty
+    float *sLen = sSuf + (a.N + 1) * VBQ_GROUP;         // [N+1][16] code lengths
+    float *sStage = sLen + (a.N + 1) * VBQ_GROUP;       // [kStages][2][U][kThreads] thread-private staging ring
+    float *myStage = sStage + threadIdx.x;
+    __shared__ double sRed[VBQ_TOTALS][kMaxThreads / 32];
+    __shared__ bool sLast;
+
+    const int N = a.N;
+    const int NS = min(N, kSmemDepth);                  // depths walked in shared memory
+    const int lam = blockIdx.y;
+    const int col = threadIdx.x & (VBQ_GROUP - 1);
+    const int rsub = threadIdx.x >> 4;
+    const bool logvar = (a.flags & VBQ_FLAG_LOGVAR) != 0;
+    const long long u0 = a.total_units * blockIdx.x / gridDim.x;
+    const long long u1 = a.total_units * (blockIdx.x + 1) / gridDim.x;
+    const int C = a.C;
+    const int rows = (int)a.rows;                       // the host splits calls so that rows*C < 2^31
+    const size_t lam_off = (size_t)lam * (size_t)a.lam_stride;
+    // byte address of tree entry (n, i) of this thread's channel = pb + V + entry_of(n,0)*64, V = 64*i + 32
+    const char *pb = reinterpret_cast<const char *>(sT) + col * 4 - 32;
+    const float *sTc = sT + col;
+    const float *sLenc = sLen + col;
+
+    double acc_len = 0.0, acc_em = 0.0, acc_dist = 0.0;
+    long long acc_level = 0;
+
+    long long unit = u0;
+    while (unit < u1) {
+        // ---- segment: a run of row passes inside one 16-channel group --------------------------------------
+        const int g = (int)(unit / a.passes);
+        const int p0 = (int)(unit - (long long)g * a.passes);
+        const int p1 = (int)min(a.passes, (long long)p0 + (u1 - unit));
+        unit += p1 - p0;
+
+        __syncthreads();
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(a.packed + (size_t)g * kPadEntries * VBQ_GROUP);
+            float4 *dst = reinterpret_cast<float4 *>(sT);
+            for (int k = threadIdx.x; k < kPadEntries * (VBQ_GROUP / 4); k += kThreads) dst[k] = __ldg(src + k);
+            if (threadIdx.x < VBQ_GROUP) {
+                const int j = threadIdx.x;
+                const int cj = min(g * VBQ_GROUP + j, C - 1);
+                const size_t po = ((size_t)lam * a.pen_channels + (a.pen_channels == 1 ? 0 : cj)) * (N + 1);
+                float suf = -CUDART_INF_F;
+                for (int n = N; n >= 0; --n) {
+                    const float np_ = -a.pen[po + n];
+                    sPen[n * VBQ_GROUP + j] = np_;
+                    sSuf[n * VBQ_GROUP + j] = suf;
+                    suf = fmaxf(suf, np_);
+                    sLen[n * VBQ_GROUP + j] = a.len ? a.len[po + n] : (float)n;
+                }
+            }
+        }
+        __syncthreads();
+
+        const int c = g * VBQ_GROUP + col;
+        const bool c_ok = c < C;
+        const int cc = min(c, C - 1);
+        const float *gT = a.table + (size_t)cc * a.Q;
+        const float *gEm = a.em ? a.em + ((size_t)lam * C + cc) * a.Q : nullptr;
+        // per-thread views of the channel-last arrays, so that the row loop only needs 32-bit element offsets
+        const float *mu_c = a.mu + cc;
+        const float *sg_c = a.sigma + cc;
+        float *zhat_c = a.zhat ? a.zhat + lam_off + cc : nullptr;
+        int *qidx_c = a.qidx ? a.qidx + lam_off + cc : nullptr;
+        int *level_c = a.level ? a.level + lam_off + cc : nullptr;
+        float *bits_c = a.bits ? a.bits + lam_off + cc : nullptr;
+        float *emb_c = a.em_bits ? a.em_bits + lam_off + cc : nullptr;
+        // this thread's channel is fixed for the segment: the penalties of the shared-memory depths live in
+        // registers (duplicated into f32x2 pairs); depths beyond N get -inf and can never be selected
+        float2 npen2[kSmemDepth + 1];
+        float thr[kSmemDepth + 1];
+#pragma unroll
+        for (int n = 0; n <= kSmemDepth; ++n) {
+            const float v = n <= N ? sPen[n * VBQ_GROUP + col] : -CUDART_INF_F;
+            npen2[n] = make_float2(v, v);
+            thr[n] = n <= N ? sSuf[n * VBQ_GROUP + col] : -CUDART_INF_F;
+        }
+        const float z0 = sTc[entry_of(0, 0) * VBQ_GROUP];
+
+        const int row_end = c_ok ? min(p1 * RP, rows) : 0;   // threads of channels >= C never pass the row test
+        int row = p0 * RP + rsub;
+        unsigned off = (unsigned)row * (unsigned)C;
+        const unsigned off_step = (unsigned)(RP * C);
+
+        // stage kStages-1 iterations ahead; every iteration commits exactly one group (possibly empty)
+        auto stage_rows = [&](int it_row, unsigned it_off, int slot) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (it_row + u * RP < row_end) {
+                    cp_async_f32(myStage + ((slot * 2 + 0) * U + u) * kThreads, mu_c + it_off + u * off_step);
+                    cp_async_f32(myStage + ((slot * 2 + 1) * U + u) * kThreads, sg_c + it_off + u * off_step);
+                }
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int k = 0; k < kStages - 1; ++k) stage_rows(row + k * U * RP, off + k * U * off_step, k);
+        int slot = 0;
+
+        for (; row - rsub < p1 * RP; row += U * RP, off += U * off_step) {
+            float mu[U], sg[U];
+            float2 nmu2[P], nsg2[P], rs2[P];   // rs2 = 1/sigma (exact mode) or -0.5/sigma^2 (fast mode)
+            cp_async_wait<kStages - 2>();        // this iteration's rows have landed
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool ok = row + u * RP < row_end;
+                mu[u] = ok ? myStage[((slot * 2 + 0) * U + u) * kThreads] : 0.0f;
+                float s = ok ? myStage[((slot * 2 + 1) * U + u) * kThreads] : 1.0f;
+                if (logvar) s = sqrtf(expf(s));
+                sg[u] = s;
+            }
+            {   // refill the slot consumed in the previous iteration
+                const int ps = slot == 0 ? kStages - 1 : slot - 1;
+                stage_rows(row + (kStages - 1) * U * RP, off + (kStages - 1) * U * off_step, ps);
+                slot = slot == kStages - 1 ? 0 : slot + 1;
+            }
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                const float r0 = __frcp_rn(sg[2 * k]), r1 = __frcp_rn(sg[2 * k + 1]);
+                nmu2[k] = make_float2(-mu[2 * k], -mu[2 * k + 1]);
+                nsg2[k] = make_float2(-sg[2 * k], -sg[2 * k + 1]);
+                rs2[k] = FAST ? make_float2(-0.5f * r0 * r0, -0.5f * r1 * r1) : make_float2(r0, r1);
+            }
+
+            // ---- depth 0: the median is the only candidate (left_0; quantizer.py:182-183) ---------------
+            float bestL[U], bestR[U];
+            int nL[U], nR[U], V[U];   // V = 64*path_index + 32 (byte offset of the path node inside its level)
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                const float2 z02 = make_float2(z0, z0);
+                const float2 s0 = FAST ? score_fast2(z02, z02, nmu2[k], rs2[k], npen2[0])
+                                       : score_exact2(z02, nmu2[k], nsg2[k], rs2[k], npen2[0]);
+                bestL[2 * k] = s0.x;
+                bestL[2 * k + 1] = s0.y;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                bestR[u] = -CUDART_INF_F;
+                nL[u] = 0;
+                nR[u] = 0;
+                V[u] = mu[u] > z0 ? 96 : 32;
+            }
+            int m_done = 0;   // deepest level processed (warp-uniform)
+
+            // ---- depths 1..10 in shared memory, fully unrolled ------------------------------------------
+#pragma unroll
+            for (int n = 1; n <= kSmemDepth; ++n) {
+                if (n > NS) break;
+                if (PRUNE && (n & 1)) {   // sound early exit: every deeper score is <= -penalty < best
+                    bool done = true;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) done = done && (fmaxf(bestL[u], bestR[u]) > thr[n - 1]);
+                    if (__all_sync(0xffffffffu, done)) break;
+                }
+                const int imm = entry_of(n, 0) * kRowStrideBytes;
+                float zp[U], zn[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const char *pa = pb + V[u];
+                    zp[u] = lds_f32(pa, imm);
+                    const int s = mu[u] > zp[u] ? 32 : -32;
+                    zn[u] = lds_f32(pa + 2 * s, imm);   // the other end of the bracket (pads at the edges)
+                    V[u] = 2 * V[u] + s;
+                }
+#pragma unroll
+                for (int k = 0; k < P; ++k) {
+                    const int u = 2 * k, v = 2 * k + 1;
+                    if (FAST) {
+                        const float2 s = score_fast2(make_float2(zp[u], zp[v]), make_float2(zn[u], zn[v]), nmu2[k],
+                                                     rs2[k], npen2[n]);
+                        if (s.x > bestL[u]) { bestL[u] = s.x; nL[u] = n; }
+                        if (s.y > bestL[v]) { bestL[v] = s.y; nL[v] = n; }
+                    } else {
+                        // roles by value: the lower of (path, neighbour) is the left bracket end
+                        const float2 zl = make_float2(fminf(zp[u], zn[u]), fminf(zp[v], zn[v]));
+                        const float2 zr = make_float2(fmaxf(zp[u], zn[u]), fmaxf(zp[v], zn[v]));
+                        const float2 sl = score_exact2(zl, nmu2[k], nsg2[k], rs2[k], npen2[n]);
+                        const float2 sr = score_exact2(zr, nmu2[k], nsg2[k], rs2[k], npen2[n]);
+                        if (sl.x > bestL[u]) { bestL[u] = sl.x; nL[u] = n; }
+                        if (sl.y > bestL[v]) { bestL[v] = sl.y; nL[v] = n; }
+                        if (sr.x > bestR[u]) { bestR[u] = sr.x; nR[u] = n; }
+                        if (sr.y > bestR[v]) { bestR[v] = sr.y; nR[v] = n; }
+                    }
+                }
+                m_done = n;
+            }
+
+            // ---- depths 11..N from the heap-order table in global memory (max_bits_per_coord > 10) --------
+            int idx[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) idx[u] = V[u] >> 6;   // path index at depth m_done + 1
+            if (DEEP && m_done == kSmemDepth) {
+                for (int n = kSmemDepth + 1; n <= N; ++n) {
+                    if (PRUNE) {
+                        bool done = true;
+                        const float th = sSuf[(n - 1) * VBQ_GROUP + col];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) done = done && (fmaxf(bestL[u], bestR[u]) > th);
+                        if (__all_sync(0xffffffffu, done)) break;
+                    }
+                    const int base = (1 << n) - 1;
+                    const float npn = sPen[n * VBQ_GROUP + col];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int ip = idx[u];
+                        const float zp = __ldg(gT + base + ip);
+                        const bool b = mu[u] > zp;
+                        const int fg = ip + (b ? 1 : 0);
+                        const int il = clamp_index(fg, n, N, false), ir = clamp_index(fg, n, N, true);
+                        const float zl = il == ip ? zp : __ldg(gT + base + il);
+                        const float zr = ir == ip ? zp : __ldg(gT + base + ir);
+                        if (FAST) {
+                            const float d = fminf(fabsf(zl - mu[u]), fabsf(zr - mu[u]));
+                            const float w = u & 1 ? rs2[u / 2].y : rs2[u / 2].x;
+                            const float s = __fmaf_rn(d * d, w, npn);
+                            if (s > bestL[u]) { bestL[u] = s; nL[u] = n; }
+                        } else {
+                            const float r = u & 1 ? rs2[u / 2].y : rs2[u / 2].x;
+                            const float sl = score_exact(zl, mu[u], sg[u], r, npn);
+                            const float sr = score_exact(zr, mu[u], sg[u], r, npn);
+                            if (sl > bestL[u]) { bestL[u] = sl; nL[u] = n; }
+                            if (sr > bestR[u]) { bestR[u] = sr; nR[u] = n; }
+                        }
+                        idx[u] = 2 * ip + (b ? 1 : 0);
+                    }
+                    m_done = n;
+                }
+            }
+
+            // ---- winner: first maximum in candidate order left_0..left_N, right_1..right_N (utils.py:401) ---
+            // Only the winning depth was tracked; its bracket is rebuilt from the final tree path (idx is the path
+            // index at depth m_done + 1), branch-free.
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool use_r = !FAST && (bestR[u] > bestL[u]);
+                const int n = use_r ? nR[u] : nL[u];
+                const int sh = m_done + 1 - n;
+                const int ipn = idx[u] >> sh;                       // path node at depth n
+                const int d = ((idx[u] >> (sh - 1)) & 1) ? 1 : -1;  // side of the other bracket end
+                const int last = (1 << n) - 1;
+                int inb = min(max(ipn + d, 0), last);
+                if (n == N && ipn + d > last) inb = max(last - 1, 0);   // no edge padding at depth N
+                float zp, zn;
+                if (!DEEP || n <= kSmemDepth) {
+                    const float *e = sTc + (entry_of(n, 0) + ipn) * VBQ_GROUP;
+                    zp = e[0];
+                    zn = e[d * VBQ_GROUP];
+                } else {
+                    zp = __ldg(gT + last + ipn);
+                    zn = __ldg(gT + last + inb);
+                }
+                bool path_wins;
+                if (FAST) {   // nearer end; the left (lower) one when equidistant
+                    const float dp = fabsf(zp - mu[u]), dn = fabsf(zn - mu[u]);
+                    path_wins = dp < dn || (dp == dn && zp <= zn);
+                } else {
+                    path_wins = use_r ? zp >= zn : zp <= zn;
+                }
+                const int i = path_wins ? ipn : inb;
+                const float zh = path_wins ? zp : zn;
+                const int q = ((2 * i + 1) << (N - n)) - 1;
+                if (row + u * RP < row_end) {
+                    const unsigned o = off + u * off_step;
+                    const float ln = sLenc[n * VBQ_GROUP];
+                    float eb = 0.0f;
+                    if (gEm) eb = __ldg(gEm + q);
+                    if (zhat_c) zhat_c[o] = zh;
+                    if (qidx_c) qidx_c[o] = q;
+                    if (level_c) level_c[o] = n;
+                    if (bits_c) bits_c[o] = ln;
+                    if (emb_c) emb_c[o] = eb;
+                    if (TOTALS) {
+                        const float r1 = FAST ? __frcp_rn(sg[u]) : (u & 1 ? rs2[u / 2].y : rs2[u / 2].x);
+                        const double t = (double)div_rn(__fsub_rn(zh, mu[u]), sg[u], r1);
+                        acc_level += n;
+                        acc_len += (double)ln;
+                        acc_em += (double)eb;
+                        acc_dist += 0.5 * t * t;
+                    }
+                }
+            }
+        }
+        cp_async_wait<0>();
+    }
+
+    if (TOTALS) {
+        double v[VBQ_TOTALS] = {(double)acc_level, acc_len, acc_em, acc_dist};
+#pragma unroll
+        for (int k = 0; k < VBQ_TOTALS; ++k) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+            if ((threadIdx.x & 31) == 0) sRed[k][threadIdx.x >> 5] = v[k];
+        }
+        __syncthreads();
+        double *part = a.partials + ((size_t)lam * kMaxGrid + blockIdx.x) * VBQ_TOTALS;
+        if (threadIdx.x < VBQ_TOTALS) {
+            double s = 0.0;
+            for (int w = 0; w < kThreads / 32; ++w) s += sRed[threadIdx.x][w];
+            part[threadIdx.x] = s;
+            __threadfence();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned t = atomicAdd(a.ticket + lam, 1u);
+            sLast = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (sLast && threadIdx.x < VBQ_TOTALS) {   // the last CTA of this lambda adds the partials in a fixed order
+            __threadfence();
+            const volatile double *p = a.partials + (size_t)lam * kMaxGrid * VBQ_TOTALS;
+            double s = a.accumulate ? a.totals[lam * VBQ_TOTALS + threadIdx.x] : 0.0;
+            for (unsigned b = 0; b < gridDim.x; ++b) s += p[b * VBQ_TOTALS + threadIdx.x];
+            a.totals[lam * VBQ_TOTALS + threadIdx.x] = s;
+            if (threadIdx.x == 0) a.ticket[lam] = 0u;
+        }
+    }
+}
+
+__global__ void selftest_divide_kernel(const float *__restrict__ x, const float *__restrict__ y, long long n,
+                                       float *__restrict__ out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride)
+        out[t] = div_rn(x[t], y[t], __frcp_rn(y[t]));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------
+extern "C" long long vbq_packed_table_floats(int C, int N) {
+    if (C < 1 || N < 0 || N > VBQ_MAX_DEPTH) return -1;
+    const long long groups = (C + VBQ_GROUP - 1) / VBQ_GROUP;
+    return groups * kPadEntries * VBQ_GROUP;
+}
+
+extern "C" int vbq_pack_code_points(const float *d_table, int C, int N, float *d_packed, void *stream) {
+    if (!d_table || !d_packed) return vbq_fail(VBQ_ERR_NULL_POINTER, "vbq_pack_code_points: null pointer");
+    if (C < 1) return vbq_fail(VBQ_ERR_BAD_SHAPE, "vbq_pack_code_points: C=%d", C);
+    RETURN_IF(vbq_check_depth(N));
+    if (((uintptr_t)d_packed & 15) != 0)
+        return vbq_fail(VBQ_ERR_MISALIGNED, "vbq_pack_code_points: d_packed not 16-byte aligned");
+    const int Q = (1 << (N + 1)) - 1;
+    const int groups = (C + VBQ_GROUP - 1) / VBQ_GROUP;
+    int grid;
+    RETURN_IF(vbq_grid_for((long long)groups * kPadEntries * VBQ_GROUP, 256, &grid));
+    pack_table_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_table, C, N, Q, groups, d_packed);
+    CUDA_TRY(cudaGetLastError());
+    return VBQ_OK;
+}
+
+// workspace = [ticket counters, padded to 256 B][per-lambda, per-CTA partial totals]
+static inline size_t ticket_bytes(int n_lambda) { return (((size_t)n_lambda * sizeof(unsigned)) + 255) & ~(size_t)255; }
+
+extern "C" long long vbq_quantize_workspace_bytes(int n_lambda) {
+    if (n_lambda < 1) return -1;
+    return (long long)ticket_bytes(n_lambda) + (long long)n_lambda * kMaxGrid * VBQ_TOTALS * (long long)sizeof(double);
+}
+
+template <bool FAST, bool PRUNE, bool TOTALS, bool DEEP, int U, int T>
+static int launch_quantize(QArgs a, int sms, cudaStream_t st) {
+    constexpr int rows_per_pass = T / VBQ_GROUP;
+    a.passes = (a.rows + rows_per_pass - 1) / rows_per_pass;
+    a.total_units = a.passes * a.n_groups;
+    // one persistent CTA per SM, each taking a contiguous span of (group, row-pass) units
+    long long gx = (a.total_units + U - 1) / U;
+    if (gx > sms) gx = sms;
+    if (gx > kMaxGrid) gx = kMaxGrid;
+    const size_t smem = ((size_t)kPadEntries * VBQ_GROUP + 3 * (size_t)(a.N + 1) * VBQ_GROUP +
+                         (size_t)kStages * 2 * U * T) * sizeof(float);
+    auto kern = vbq_quantize_kernel<FAST, PRUNE, TOTALS, DEEP, U, T>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3((int)gx, a.n_lambda), T, smem, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    return VBQ_OK;
+}
+
+template <bool FAST, bool PRUNE, int U, int T>
+static int launch_mode2(const QArgs &a, int sms, cudaStream_t st) {
+    const bool tot = a.totals != nullptr, deep = a.N > kSmemDepth;
+    if (deep) return tot ? launch_quantize<FAST, PRUNE, true, true, U, T>(a, sms, st)
+                         : launch_quantize<FAST, PRUNE, false, true, U, T>(a, sms, st);
+    return tot ? launch_quantize<FAST, PRUNE, true, false, U, T>(a, sms, st)
+               : launch_quantize<FAST, PRUNE, false, false, U, T>(a, sms, st);
+}
+
+template <int U, int T>
+static int launch_mode(const QArgs &a, int sms, cudaStream_t st) {
+    const bool fast = (a.flags & VBQ_FLAG_FAST) != 0, prune = !(a.flags & VBQ_FLAG_NO_PRUNE);
+    if (fast) return prune ? launch_mode2<true, true, U, T>(a, sms, st) : launch_mode2<true, false, U, T>(a, sms, st);
+    return prune ? launch_mode2<false, true, U, T>(a, sms, st) : launch_mode2<false, false, U, T>(a, sms, st);
+}
+
+extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long rows, int C, const float *d_table,
+                            const float *d_packed, int N, const float *d_penalty, const float *d_length, int n_lambda,
+                            int pen_channels, const float *d_entropy_model, float *d_zhat, int *d_qidx, int *d_level,
+                            float *d_bits, float *d_em_bits, double *d_totals, void *d_workspace,
+                            long long workspace_bytes, unsigned flags, void *stream) {
+    if (rows < 0 || C < 1 || n_lambda < 1 || n_lambda > 65535 || (pen_channels != 1 && pen_channels != C))
+        return vbq_fail(VBQ_ERR_BAD_SHAPE, "vbq_quantize: rows=%lld C=%d n_lambda=%d pen_channels=%d", rows, C,
+                        n_lambda, pen_channels);
+    RETURN_IF(vbq_check_depth(N));
+    if (flags & ~(VBQ_FLAG_LOGVAR | VBQ_FLAG_NO_PRUNE | VBQ_FLAG_FAST))
+        return vbq_fail(VBQ_ERR_BAD_FLAGS, "vbq_quantize: unknown flag bits 0x%x", flags);
+    if (!d_table || !d_packed || !d_penalty || (rows > 0 && (!d_mu || !d_sigma)))
+        return vbq_fail(VBQ_ERR_NULL_POINTER, "vbq_quantize: null input pointer");
+    if (d_em_bits && !d_entropy_model)
+        return vbq_fail(VBQ_ERR_NULL_POINTER, "vbq_quantize: d_em_bits requested without d_entropy_model");
+    if (((uintptr_t)d_packed & 15) != 0)
+        return vbq_fail(VBQ_ERR_MISALIGNED, "vbq_quantize: d_packed not 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+
+    QArgs a;
+    a.mu = d_mu; a.sigma = d_sigma; a.rows = rows; a.C = C;
+    a.table = d_table; a.packed = d_packed;
+    a.N = N; a.Q = (1 << (N + 1)) - 1;
+    a.pen = d_penalty; a.len = d_length; a.n_lambda = n_lambda; a.pen_channels = pen_channels;
+    a.em = d_entropy_model;
+    a.zhat = d_zhat; a.qidx = d_qidx; a.level = d_level; a.bits = d_bits; a.em_bits = d_em_bits;
+    a.totals = d_totals; a.partials = nullptr; a.ticket = nullptr;
+    a.flags = flags;
+    a.n_groups = (C + VBQ_GROUP - 1) / VBQ_GROUP;
+
+    if (d_totals) {
+        const long long need = vbq_quantize_workspace_bytes(n_lambda);
+        if (!d_workspace || workspace_bytes < need)
+            return vbq_fail(VBQ_ERR_WORKSPACE, "vbq_quantize: totals need a %lld-byte workspace (got %lld)", need,
+                            workspace_bytes);
+        if (((uintptr_t)d_workspace & 255) != 0)
+            return vbq_fail(VBQ_ERR_MISALIGNED, "vbq_quantize: workspace not 256-byte aligned");
+        a.ticket = (unsigned *)d_workspace;
+        a.partials = (double *)((char *)d_workspace + ticket_bytes(n_lambda));
+        CUDA_TRY(cudaMemsetAsync(a.ticket, 0, (size_t)n_lambda * sizeof(unsigned), st));
+    }
+    if (rows == 0) {
+        if (d_totals) CUDA_TRY(cudaMemsetAsync(d_totals, 0, (size_t)n_lambda * VBQ_TOTALS * sizeof(double), st));
+        return VBQ_OK;
+    }
+
+    int dev = 0, sms = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    // tuning override (development only): VBQ_TUNE=<U><threads/256>, e.g. 22 = U 2, 512 threads
+    int tune = 22;
+    if (const char *e = getenv("VBQ_TUNE")) tune = atoi(e);
+    // the kernel indexes a channel-last array with 32-bit element offsets: split very large calls into row chunks
+    const long long max_chunk_rows = ((1ll << 31) - 1) / C > 1 ? (((1ll << 31) - 1) / C) & ~1023ll : 1;
+    a.lam_stride = rows * (long long)C;
+    for (long long r0 = 0; r0 < rows; r0 += max_chunk_rows) {
+        const long long nr = rows - r0 < max_chunk_rows ? rows - r0 : max_chunk_rows;
+        const size_t eo = (size_t)r0 * C;
+        QArgs b = a;
+        b.rows = nr;
+        b.mu = d_mu + eo;
+        b.sigma = d_sigma + eo;
+        if (d_zhat) b.zhat = d_zhat + eo;
+        if (d_qidx) b.qidx = d_qidx + eo;
+        if (d_level) b.level = d_level + eo;
+        if (d_bits) b.bits = d_bits + eo;
+        if (d_em_bits) b.em_bits = d_em_bits + eo;
+        b.accumulate = r0 > 0;
+        int st_;
+        switch (tune) {
+            case 23: st_ = launch_mode<2, 768>(b, sms, st); break;
+            case 42: st_ = launch_mode<4, 512>(b, sms, st); break;
+            case 41: st_ = launch_mode<4, 256>(b, sms, st); break;
+            default: st_ = launch_mode<2, 512>(b, sms, st); break;
+        }
+        RETURN_IF(st_);
+    }
+    return VBQ_OK;
+}
+
+extern "C" int vbq_selftest_divide(const float *d_a, const float *d_b, long long n, float *d_out, void *stream) {
+    if (n > 0 && (!d_a || !d_b || !d_out)) return vbq_fail(VBQ_ERR_NULL_POINTER, "vbq_selftest_divide: null pointer");
+    if (n < 0) return vbq_fail(VBQ_ERR_BAD_SHAPE, "vbq_selftest_divide: n=%lld", n);
+    if (n == 0) return VBQ_OK;
+    int grid;
+    RETURN_IF(vbq_grid_for(n, 256, &grid));
+    selftest_divide_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_a, d_b, n, d_out);
+    CUDA_TRY(cudaGetLastError());
+    return VBQ_OK;
+}
