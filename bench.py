@@ -273,33 +273,41 @@ def run_ours(args, rank, world, local_rank):
     total_ms = float(t.item())
     value = COORDS * world * args.steps / (total_ms * 1e-3)
 
-    # end-to-end through the reference-facing call with HOST buffers (pinned), H2D + D2H inside the timed region
+    # end-to-end through the C-ABI host entry point (vbq_quantize_host, what the reference-facing
+    # compress_batch_channel_latents runs for host arrays): HOST pinned buffers in, HOST pinned buffers out, the
+    # upload / kernel / download of row chunks overlapped on three streams, all inside the timed region.
     h_mu = [b["mu"].cpu().pin_memory() for b in sets[:2]]
     h_sigma = [b["sigma"].cpu().pin_memory() for b in sets[:2]]
-    h_q = torch.empty((ROWS, C), dtype=torch.int32).pin_memory()
-    h_b = torch.empty((ROWS, C), dtype=torch.float32).pin_memory()
+    h_q = torch.empty((1, ROWS, C), dtype=torch.int32).pin_memory()
+    h_b = torch.empty((1, ROWS, C), dtype=torch.float32).pin_memory()
     h_tot = torch.empty((1, 4), dtype=torch.float64).pin_memory()
+    pipe = ops.HostPipeline(C, N_BITS, 1, args.chunk_rows, ops.OUT_QIDX | ops.OUT_BITS | ops.OUT_TOTALS, device=dev)
 
     def e2e_step(i):
-        b = sets[i % n_sets]
-        b["mu"].copy_(h_mu[i % 2], non_blocking=True)
-        b["sigma"].copy_(h_sigma[i % 2], non_blocking=True)
-        step(i)
-        h_q.copy_(b["qidx"][0], non_blocking=True)
-        h_b.copy_(b["bits"][0], non_blocking=True)
-        h_tot.copy_(totals, non_blocking=True)
-        torch.cuda.synchronize()
+        pipe.run(h_mu[i % 2], h_sigma[i % 2], q.all_code_points, q._packed, pen, length, None,
+                 qidx=h_q, bits=h_b, totals=h_tot, flags=args.flags)
+        if world > 1:
+            t_ = h_tot.to(dev)
+            sharding.all_reduce_totals(t_)
+            h_tot.copy_(t_)
         return float(h_tot[0, 1])
 
-    e2e_steps = max(3, min(args.steps, 10))
+    e2e_steps = max(3, min(args.steps, 20))
     for i in range(2):
         e2e_step(i)
+    # the pipeline must reproduce the device-resident results exactly
+    step(0)
+    torch.cuda.synchronize()
+    pipe.run(h_mu[0], h_sigma[0], q.all_code_points, q._packed, pen, length, None, qidx=h_q, bits=h_b, totals=h_tot,
+             flags=args.flags)
+    assert torch.equal(h_q[0], sets[0]["qidx"][0].cpu()) and torch.equal(h_b[0], sets[0]["bits"][0].cpu())
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         e2e_step(i)
     barrier()
     e2e_s = time.perf_counter() - t0
+    pipe.close()
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -333,7 +341,8 @@ def run_ours(args, rank, world, local_rank):
                      "algorithmic_bytes_per_launch": COORDS * BYTES_PER_COORD},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * COORDS * 4,
-                "d2h_bytes_per_step": 2 * COORDS * 4 + 32, "steps": e2e_steps},
+                "d2h_bytes_per_step": 2 * COORDS * 4 + 32, "steps": e2e_steps,
+                "api": "vbq_quantize_host (pinned host in/out, %d-row chunks, 3 streams)" % args.chunk_rows},
         "gpu_launches": args.steps,
         "clocks": clocks.summary(),
     }
@@ -347,6 +356,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--flags", type=int, default=0, help="VBQ_FLAG_* bits passed to vbq_quantize")
+    ap.add_argument("--chunk-rows", type=int, default=4608, help="rows per chunk of the host pipeline (e2e leg)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -53,6 +53,7 @@ enum {
 /* flags of vbq_quantize */
 #define VBQ_FLAG_LOGVAR   1u     /* d_sigma holds log-variances; sigma = sqrt(exp(logvar)) (quantizer.py:193-198) */
 #define VBQ_FLAG_NO_PRUNE 2u     /* visit every bit depth even when deeper levels provably cannot win */
+#define VBQ_FLAG_ACCUMULATE_TOTALS 8u /* add this call's sums to d_totals instead of overwriting them */
 #define VBQ_FLAG_FAST     4u     /* score with d*d*(0.5/sigma^2) + pen on the nearer bracket end only (not bit-faithful
                                     to utils.py:318-320 rounding; differs only inside float32 rounding ties) */
 
@@ -111,6 +112,35 @@ int vbq_quantize(const float *d_mu, const float *d_sigma, long long rows, int C,
                  float *d_zhat, int *d_qidx, int *d_level, float *d_bits, float *d_em_bits,
                  double *d_totals, void *d_workspace, long long workspace_bytes,
                  unsigned flags, void *stream);
+
+/* ---- the hot path for host-resident latents ---------------------------------------------------------------- */
+
+/* output selection bits of vbq_host_ctx_create */
+#define VBQ_OUT_ZHAT    1u
+#define VBQ_OUT_QIDX    2u
+#define VBQ_OUT_LEVEL   4u
+#define VBQ_OUT_BITS    8u
+#define VBQ_OUT_EM_BITS 16u
+#define VBQ_OUT_TOTALS  32u
+
+/* A context owns three device staging slots of `chunk_rows` rows (inputs plus the selected outputs for n_lambda
+ * trade-offs), three streams and the totals workspace.  It is the only object of this library that allocates;
+ * one context serves one calling thread at a time. */
+typedef struct vbq_host_ctx vbq_host_ctx;
+int vbq_host_ctx_create(int C, int N, int n_lambda, long long chunk_rows, unsigned outputs, vbq_host_ctx **out);
+int vbq_host_ctx_destroy(vbq_host_ctx *ctx);
+
+/* vbq_quantize for HOST arrays (pinned memory recommended): the reference's host-side call
+ * compress_batch_channel_latents(batch_means, batch_stds, lambs) on NumPy inputs (quantizer.py:156-188).
+ * h_mu / h_sigma are (rows, C); outputs are (n_lambda, rows, C) host arrays (NULL to skip; must have been
+ * selected at context creation); h_totals is (n_lambda, VBQ_TOTALS).  Tables, penalties and entropy models are
+ * device pointers as in vbq_quantize.  Rows are processed in chunks whose upload, kernel and download overlap on
+ * three streams; the call returns when all results are in host memory. */
+int vbq_quantize_host(vbq_host_ctx *ctx, const float *h_mu, const float *h_sigma, long long rows,
+                      const float *d_table, const float *d_packed, const float *d_penalty, const float *d_length,
+                      int pen_channels, const float *d_entropy_model,
+                      float *h_zhat, int *h_qidx, int *h_level, float *h_bits, float *h_em_bits, double *h_totals,
+                      unsigned flags);
 
 /* Self-test helper: out[i] = the kernel's division a[i]/b[i] (reciprocal + FMA correction) so that tests can
  * compare it with IEEE division bit for bit. */

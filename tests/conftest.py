@@ -16,8 +16,8 @@ def pytest_configure(config):
 @pytest.fixture(scope="session", autouse=True)
 def _built_library():
     """Every test session builds (or re-uses) the in-tree CUDA library; nvcc cross-compiles without a GPU."""
-    from vbq_b200 import build
-    build.build_library()
+    import __graft_entry__ as g
+    g._load_build_module().build_library()
 
 
 def pytest_collection_modifyitems(config, items):

@@ -159,3 +159,29 @@ def test_prune_equals_no_prune_large():
     for x, y in zip(a, b):
         assert np.array_equal(x["zk"], y["zk"]) and np.array_equal(x["lk"], y["lk"])
         assert np.array_equal(x["zk"], x["zo"])
+
+
+def test_host_pipeline_matches_device_path():
+    """vbq_quantize_host (chunked upload/kernel/download) == vbq_quantize on the same data, incl. ragged last chunk."""
+    import vbq_b200
+    from vbq_b200 import ops
+    C, N, rows = 40, 10, 5000
+    lambs = [2.0 ** -5, 0.5, 16.0]
+    pr = H.make_prior(C, seed=5)
+    q = vbq_b200.ChannelwisePriorCDFQuantizer(C, N)
+    q.set_code_points(ops.build_code_points_learned(_dev(pr.packed()), N))
+    mu, sigma, _ = H.make_latents(pr, rows, 6, table=q.all_code_points.cpu().numpy())
+    want = q.quantize(_dev(mu), _dev(sigma), lambs,
+                      outputs=ops.OUT_ZHAT | ops.OUT_QIDX | ops.OUT_LEVEL | ops.OUT_BITS | ops.OUT_TOTALS)
+    pen, length = q._length_tables(lambs)
+    L = len(lambs)
+    h = dict(zhat=torch.empty((L, rows, C)).pin_memory(), qidx=torch.empty((L, rows, C), dtype=torch.int32).pin_memory(),
+             level=torch.empty((L, rows, C), dtype=torch.int32), bits=torch.empty((L, rows, C)),
+             totals=torch.empty((L, 4), dtype=torch.float64))
+    pipe = ops.HostPipeline(C, N, L, 768, ops.OUT_ZHAT | ops.OUT_QIDX | ops.OUT_LEVEL | ops.OUT_BITS | ops.OUT_TOTALS)
+    pipe.run(torch.from_numpy(mu).pin_memory(), sigma, q.all_code_points, q._packed, pen, length, None, **h)
+    pipe.close()
+    for k in ("zhat", "qidx", "level", "bits"):
+        assert torch.equal(h[k], want[k].cpu()), k
+    # chunked accumulation changes the float64 summation order only
+    assert torch.allclose(h["totals"], want["totals"].cpu(), rtol=1e-12, atol=0)

@@ -13,6 +13,7 @@ OK = 0
 FLAG_LOGVAR = 1
 FLAG_NO_PRUNE = 2
 FLAG_FAST = 4
+FLAG_ACCUMULATE_TOTALS = 8
 GROUP = 16
 TOTALS = 4
 PRIOR_PARAMS = 43
@@ -45,6 +46,9 @@ SIGNATURES = {
     "vbq_quantize_workspace_bytes": (_ll, [_i]),
     "vbq_quantize": (_i, [_p, _p, _ll, _i, _p, _p, _i, _p, _p, _i, _i, _p,
                           _p, _p, _p, _p, _p, _p, _p, _ll, _u, _p]),
+    "vbq_host_ctx_create": (_i, [_i, _i, _i, _ll, _u, C.POINTER(C.c_void_p)]),
+    "vbq_host_ctx_destroy": (_i, [_p]),
+    "vbq_quantize_host": (_i, [_p, _p, _p, _ll, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _u]),
     "vbq_selftest_divide": (_i, [_p, _p, _ll, _p, _p]),
 }
 

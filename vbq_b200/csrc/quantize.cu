@@ -554,7 +554,7 @@ extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long r
         return vbq_fail(VBQ_ERR_BAD_SHAPE, "vbq_quantize: rows=%lld C=%d n_lambda=%d pen_channels=%d", rows, C,
                         n_lambda, pen_channels);
     RETURN_IF(vbq_check_depth(N));
-    if (flags & ~(VBQ_FLAG_LOGVAR | VBQ_FLAG_NO_PRUNE | VBQ_FLAG_FAST))
+    if (flags & ~(VBQ_FLAG_LOGVAR | VBQ_FLAG_NO_PRUNE | VBQ_FLAG_FAST | VBQ_FLAG_ACCUMULATE_TOTALS))
         return vbq_fail(VBQ_ERR_BAD_FLAGS, "vbq_quantize: unknown flag bits 0x%x", flags);
     if (!d_table || !d_packed || !d_penalty || (rows > 0 && (!d_mu || !d_sigma)))
         return vbq_fail(VBQ_ERR_NULL_POINTER, "vbq_quantize: null input pointer");
@@ -612,7 +612,7 @@ extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long r
         if (d_level) b.level = d_level + eo;
         if (d_bits) b.bits = d_bits + eo;
         if (d_em_bits) b.em_bits = d_em_bits + eo;
-        b.accumulate = r0 > 0;
+        b.accumulate = r0 > 0 || (flags & VBQ_FLAG_ACCUMULATE_TOTALS);
         int st_;
         switch (tune) {
             case 23: st_ = launch_mode<2, 768>(b, sms, st); break;

@@ -276,3 +276,70 @@ def selftest_divide(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     st = _lib.load().vbq_selftest_divide(_ptr(a), _ptr(b), a.numel(), _ptr(out), _stream(a.device))
     _lib.check(st, "vbq_selftest_divide")
     return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# host-resident latents: chunked upload / kernel / download pipeline (vbq_quantize_host)
+# ------------------------------------------------------------------------------------------------------
+def _host_ptr(x, dtype, shape, name):
+    """Pointer of a contiguous CPU tensor / ndarray (pinned memory recommended); None passes through."""
+    if x is None:
+        return None
+    t = x if isinstance(x, torch.Tensor) else torch.from_numpy(x)
+    if t.is_cuda:
+        raise RuntimeError("vbq_b200: `%s` must live in host memory for the host pipeline" % name)
+    if t.dtype != dtype or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
+        raise ValueError("vbq_b200: `%s` must be a contiguous %s host array of shape %s" % (name, dtype, tuple(shape)))
+    return t.data_ptr()
+
+
+class HostPipeline:
+    """Owns a `vbq_host_ctx`: three device staging slots + three streams.  `run` quantizes host arrays chunk by
+    chunk with upload, kernel and download overlapped, and returns when the results are in host memory."""
+
+    def __init__(self, num_channels, max_bits, n_lambda, chunk_rows, outputs, device=None):
+        import ctypes
+        self._lib = _lib.load()
+        self.C, self.N, self.L = int(num_channels), int(max_bits), int(n_lambda)
+        self.outputs = int(outputs)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            st = self._lib.vbq_host_ctx_create(self.C, self.N, self.L, int(chunk_rows), self.outputs,
+                                               ctypes.byref(handle))
+        _lib.check(st, "vbq_host_ctx_create")
+        self._h = handle
+
+    def run(self, h_mu, h_sigma, table, packed, penalty, length=None, entropy_model=None, zhat=None, qidx=None,
+            level=None, bits=None, em_bits=None, totals=None, flags=0):
+        if self._h is None:
+            raise RuntimeError("vbq_b200: HostPipeline is closed")
+        rows = int(h_mu.shape[0])
+        L, C = self.L, self.C
+        _need_cuda("table", table, torch.float32, 2)
+        _need_cuda("packed", packed, torch.float32)
+        _need_cuda("penalty", penalty, torch.float32, 3)
+        if penalty.shape[0] != L or penalty.shape[2] != self.N + 1 or penalty.shape[1] not in (1, C):
+            raise ValueError("vbq_b200: penalty must be (n_lambda, 1 or C, N+1)")
+        o = (L, rows, C)
+        with torch.cuda.device(self.device):
+            st = self._lib.vbq_quantize_host(
+                self._h, _host_ptr(h_mu, torch.float32, (rows, C), "h_mu"),
+                _host_ptr(h_sigma, torch.float32, (rows, C), "h_sigma"), rows, _ptr(table), _ptr(packed),
+                _ptr(penalty), _ptr(length), int(penalty.shape[1]), _ptr(entropy_model),
+                _host_ptr(zhat, torch.float32, o, "zhat"), _host_ptr(qidx, torch.int32, o, "qidx"),
+                _host_ptr(level, torch.int32, o, "level"), _host_ptr(bits, torch.float32, o, "bits"),
+                _host_ptr(em_bits, torch.float32, o, "em_bits"),
+                _host_ptr(totals, torch.float64, (L, _lib.TOTALS), "totals"), flags)
+        _lib.check(st, "vbq_quantize_host")
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            self._lib.vbq_host_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
