@@ -455,3 +455,42 @@ def rd_totals(Z, S, Z_hat, bits):
     posterior-weighted squared error sum (z_hat-mu)^2/(2 sigma^2), float64."""
     d = (Z_hat.astype(np.float64) - Z.astype(np.float64)) / S.astype(np.float64)
     return float(np.sum(bits, dtype=np.float64)), float(0.5 * np.sum(d * d))
+
+
+# ----------------------------------------------------------------------------------------------
+# Generic forms used by the golden-vector tests
+# ----------------------------------------------------------------------------------------------
+def bracket_search_f64(mu, sigma, lamb, codepoints_heap, N):
+    """Algorithm 1 in z-space, float64: maximise -0.5((z-mu)/sigma)^2 - lamb*n over the bracketing candidates of a
+    single shared prior (what utils.encode_vectorized computes in xi-space, utils.py:263-304).  Returns
+    (z_hat, num_bits)."""
+    mu = np.asarray(mu, dtype=np.float64)
+    sigma = np.asarray(sigma, dtype=np.float64)
+    best = np.full(mu.shape, -np.inf)
+    zhat = np.zeros(mu.shape)
+    bits = np.zeros(mu.shape, dtype=np.int64)
+    for n in range(N + 1):
+        grid = codepoints_heap[2 ** n - 1: 2 ** (n + 1) - 1]
+        r = np.clip(np.searchsorted(grid, mu, side="left"), 0, 2 ** n - 1)
+        l = np.clip(r - 1, 0, 2 ** n - 1)
+        for idx in (l, r):
+            s = -0.5 * ((grid[idx] - mu) / sigma) ** 2 - lamb * n
+            upd = s > best
+            best = np.where(upd, s, best)
+            zhat = np.where(upd, grid[idx], zhat)
+            bits = np.where(upd, n, bits)
+    return zhat, bits
+
+
+def batch_quantize_indep_dims(P, L, loc, scale, lambs):
+    """utils.batch_quantize_indep_dims (utils.py:363-423) for explicit candidates P, L of shape (M, B, K) and the
+    float32 Gaussian `fun` of curry_normal_logpdf; returns dicts of (B, K) arrays."""
+    P = np.asarray(P, dtype=F32)
+    fun_P = F32(-0.5) * ((P - np.asarray(loc, dtype=F32)) / np.asarray(scale, dtype=F32)) ** 2
+    Zh, nb = {}, {}
+    for lamb in lambs:
+        scores = fun_P - lamb * L
+        k = np.argmax(scores, axis=0)
+        Zh[lamb] = np.take_along_axis(P, k[None], axis=0)[0]
+        nb[lamb] = np.take_along_axis(L, k[None], axis=0)[0]
+    return Zh, nb
