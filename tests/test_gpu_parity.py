@@ -185,3 +185,30 @@ def test_host_pipeline_matches_device_path():
         assert torch.equal(h[k], want[k].cpu()), k
     # chunked accumulation changes the float64 summation order only
     assert torch.allclose(h["totals"], want["totals"].cpu(), rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("N,C,rows,n_lambda,corrected", [(10, 24, 900, 16, False), (10, 20, 500, 100, True),
+                                                         (5, 7, 333, 3, False)])
+@pytest.mark.parametrize("fast", [0, 4])
+def test_sweep_equals_per_lambda_walks(N, C, rows, n_lambda, corrected, fast):
+    """One walk serving all lambdas (sweep kernel, incl. lambda chunking at 100 lambdas) gives exactly the outputs
+    of one walk per lambda (VBQ_FLAG_NO_SWEEP); totals agree to 1e-6 (the sweep derives the winner's distortion from
+    its float32 score)."""
+    import vbq_b200
+    from vbq_b200 import ops
+    pr = H.make_prior(C, seed=N)
+    q = vbq_b200.ChannelwisePriorCDFQuantizer(C, N)
+    q.set_code_points(ops.build_code_points_learned(_dev(pr.packed()), N))
+    mu, sigma, _ = H.make_latents(pr, rows, 9, table=q.all_code_points.cpu().numpy())
+    lambs = [float(l) for l in 2 ** np.linspace(-8, 7, n_lambda)]
+    if corrected:
+        rng = np.random.default_rng(0)
+        q.raw_code_length_entropy_models = {l: rng.uniform(0.5, 6.0, (C, N + 1)).astype(np.float32) for l in lambs}
+        q.entropy_models = {l: rng.uniform(0.5, 12.0, (C, q.quantization_levels)).astype(np.float32) for l in lambs}
+    outs = ops.OUT_ZHAT | ops.OUT_QIDX | ops.OUT_LEVEL | ops.OUT_BITS | ops.OUT_TOTALS
+    a = q.quantize(_dev(mu), _dev(sigma), lambs, outputs=outs, flags=fast, entropy_bits=corrected)
+    b = q.quantize(_dev(mu), _dev(sigma), lambs, outputs=outs, flags=fast | ops.FLAG_NO_SWEEP, entropy_bits=corrected)
+    for k in ("zhat", "qidx", "level", "bits", "em_bits"):
+        assert torch.equal(a[k], b[k]), k
+    assert torch.allclose(a["totals"], b["totals"], rtol=1e-6, atol=1e-9)
+    assert torch.equal(a["totals"][:, :3], b["totals"][:, :3])     # integer / float sums of identical terms

@@ -14,6 +14,7 @@ FLAG_LOGVAR = 1
 FLAG_NO_PRUNE = 2
 FLAG_FAST = 4
 FLAG_ACCUMULATE_TOTALS = 8
+FLAG_NO_SWEEP = 16
 GROUP = 16
 TOTALS = 4
 PRIOR_PARAMS = 43

@@ -21,6 +21,7 @@ OUT_TOTALS = 32
 FLAG_LOGVAR = _lib.FLAG_LOGVAR
 FLAG_NO_PRUNE = _lib.FLAG_NO_PRUNE
 FLAG_FAST = _lib.FLAG_FAST
+FLAG_NO_SWEEP = _lib.FLAG_NO_SWEEP
 
 
 def _ptr(t: Optional[torch.Tensor]):
