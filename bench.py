@@ -48,45 +48,56 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md)."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled every ~2 ms WHILE the timed region runs (NVML; the fields are the ones
+    of the recipe's `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*` line)."""
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                     "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                     "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                     "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+
+            def loop():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                        for k, bit in names.items():
+                            if r & bit:
+                                self.reasons.add(k)
+                    except Exception:
+                        pass
+                    time.sleep(0.002)
+
+            self._thread = threading.Thread(target=loop, daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
+            self._thread = None
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
     def __exit__(self, *a):
-        if self.proc is not None:
-            time.sleep(0.12)
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1)
 
     def summary(self):
-        good = [r for r in self.rows if len(r) == 6 and r[0].isdigit()]
-        if not good:
+        if not self.samples:
             return None
-        sm = sorted(int(r[0]) for r in good)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in good)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(good[0][1]), "reasons": reasons, "samples": len(good)}
+        sm = sorted(self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(sm)}
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -316,6 +327,11 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     peaks, peak_kind = measured_peaks()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")   # dram__bytes_read+write of one ncu --set full capture
+    if os.path.exists(tp) and args.flags == 0:
+        with open(tp) as f:
+            traffic = json.load(f)["traffic_bytes_per_launch"]
     kern_ms = float(np.median(per_launch_ms))
     achieved = COORDS * BYTES_PER_COORD / (kern_ms * 1e-3) / 1e9
     cpu = None
@@ -336,7 +352,7 @@ def run_ours(args, rank, world, local_rank):
                    "l2": "%d rotating input/output sets (%d MB) > 126 MB L2" % (n_sets, n_sets * set_bytes >> 20),
                    "flags": args.flags, "parallelism": "dp%d, one all-reduce of (n_lambda,4) f64 totals" % world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
                      "kernel": "vbq_quantize_kernel", "kernel_ms": kern_ms,
                      "algorithmic_bytes_per_launch": COORDS * BYTES_PER_COORD},
         "cpu_baseline": cpu,
@@ -352,7 +368,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--flags", type=int, default=0, help="VBQ_FLAG_* bits passed to vbq_quantize")

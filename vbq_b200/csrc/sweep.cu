@@ -6,6 +6,8 @@
 // score = fl(h + (-pen[lambda][c][n])) is bit-identical to the reference's fl(fl(-0.5 t^2) - fl(lambda*len)).
 // Used by vbq_quantize when n_lambda > 1 and max_bits_per_coord <= 10; the per-lambda results are identical to the
 // single-lambda kernel (tests/test_gpu_parity.py::test_sweep_equals_per_lambda_walks).
+#include <stdlib.h>
+
 #include "tree.cuh"
 
 // h = fl(-0.5 * fl(t^2)), t = fl(fl(z - mu) / sigma): the lambda-independent part of utils.py:318-320
@@ -23,7 +25,7 @@ __device__ __forceinline__ float2 distortion_fast2(float2 zp, float2 zn, float2 
     return __fmul2_rn(__fmul2_rn(d, d), nw);
 }
 
-template <bool FAST, bool TOTALS, int kThreads>
+template <bool FAST, bool TOTALS, int kThreads, int LP>
 __global__ void __launch_bounds__(kThreads, 1) vbq_sweep_kernel(const QArgs a) {
     constexpr int U = 2;                                  // one f32x2 pair of coordinates per thread
     constexpr int RP = kThreads / VBQ_GROUP;
@@ -32,8 +34,8 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_sweep_kernel(const QArgs a) {
     const int L = a.n_lambda;
     float *sT = smem;                                     // [kPadEntries][16]
     float *sPen = sT + kPadEntries * VBQ_GROUP;           // [L][N+1][16] negated penalties
-    float *sLen = sPen + (size_t)L * (N + 1) * VBQ_GROUP; // [L][N+1][16] code lengths
-    float *sStage = sLen + (size_t)L * (N + 1) * VBQ_GROUP;   // [kStages][2][U][kThreads]
+    float *sLen = sPen + (size_t)L * (N + 1) * VBQ_GROUP; // [L][N+1][16] code lengths (only if a.len is given)
+    float *sStage = sLen + (a.len ? (size_t)L * (N + 1) * VBQ_GROUP : 0);   // [kStages][2][U][kThreads]
     double *sAcc = reinterpret_cast<double *>(sStage + kStages * 2 * U * kThreads);   // [warps][L][4]
     float *myStage = sStage + threadIdx.x;
     __shared__ bool sLast;
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_sweep_kernel(const QArgs a) {
                 const int cj = min(g * VBQ_GROUP + j, C - 1);
                 const size_t po = ((size_t)lam * a.pen_channels + (a.pen_channels == 1 ? 0 : cj)) * (N + 1) + n;
                 sPen[k] = -a.pen[po];
-                sLen[k] = a.len ? a.len[po] : (float)n;
+                if (a.len) sLen[k] = a.len[po];
             }
         }
         __syncthreads();
@@ -158,94 +160,105 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_sweep_kernel(const QArgs a) {
             }
             const int idx[U] = {V[0] >> 6, V[1] >> 6};   // path index at depth N + 1
 
-            // ---- every lambda from the registers -----------------------------------------------------------
-            for (int lam = 0; lam < L; ++lam) {
-                const float *pl = sPen + (size_t)lam * (N + 1) * VBQ_GROUP + col;
-                float bL[U], bR[U];
-                int nL[U], nR[U];
-                {
-                    const float np0 = pl[0];
-                    bL[0] = hL[0].x + np0;
-                    bL[1] = hL[0].y + np0;
-                    bR[0] = bR[1] = -CUDART_INF_F;
-                    nL[0] = nL[1] = nR[0] = nR[1] = 0;
+            // ---- every lambda from the registers, LP lambdas at a time (independent running maxima => ILP) ------
+            for (int lam0 = 0; lam0 < L; lam0 += LP) {
+                float bL[LP][U], bR[LP][U];
+                int nL[LP][U], nR[LP][U];
+                const float *pl[LP];
+#pragma unroll
+                for (int j = 0; j < LP; ++j) {
+                    const int lam = min(lam0 + j, L - 1);   // a ragged last group recomputes the last lambda
+                    pl[j] = sPen + (size_t)lam * (N + 1) * VBQ_GROUP + col;
+                    const float np0 = pl[j][0];
+                    bL[j][0] = hL[0].x + np0;
+                    bL[j][1] = hL[0].y + np0;
+                    bR[j][0] = bR[j][1] = -CUDART_INF_F;
+                    nL[j][0] = nL[j][1] = nR[j][0] = nR[j][1] = 0;
                 }
 #pragma unroll
                 for (int n = 1; n <= kSmemDepth; ++n) {
                     if (n > N) break;
-                    const float npn = pl[n * VBQ_GROUP];
-                    const float2 sl = __fadd2_rn(hL[n], make_float2(npn, npn));
-                    if (sl.x > bL[0]) { bL[0] = sl.x; nL[0] = n; }
-                    if (sl.y > bL[1]) { bL[1] = sl.y; nL[1] = n; }
-                    if (!FAST) {
-                        const float2 sr = __fadd2_rn(hR[n], make_float2(npn, npn));
-                        if (sr.x > bR[0]) { bR[0] = sr.x; nR[0] = n; }
-                        if (sr.y > bR[1]) { bR[1] = sr.y; nR[1] = n; }
-                    }
-                }
-                double t_len = 0.0, t_em = 0.0, t_dist = 0.0;
-                int t_level = 0;
-                const size_t lam_off = (size_t)lam * (size_t)a.lam_stride;
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const bool use_r = !FAST && (bR[u] > bL[u]);
-                    const int n = use_r ? nR[u] : nL[u];
-                    const float best = use_r ? bR[u] : bL[u];
-                    const float ln = sLen[((size_t)lam * (N + 1) + n) * VBQ_GROUP + col];
-                    float eb = 0.0f;
-                    if (any_out || a.em) {
-                        // rebuild the bracket of depth n from the final path (see quantize.cu)
-                        const int sh = N + 1 - n;
-                        const int ipn = idx[u] >> sh;
-                        const int d = ((idx[u] >> (sh - 1)) & 1) ? 1 : -1;
-                        const int last = (1 << n) - 1;
-                        int inb = min(max(ipn + d, 0), last);
-                        if (n == N && ipn + d > last) inb = max(last - 1, 0);
-                        const float *e = sTc + (entry_of(n, 0) + ipn) * VBQ_GROUP;
-                        const float zp = e[0], zn = e[d * VBQ_GROUP];
-                        bool path_wins;
-                        if (FAST) {
-                            const float dp = fabsf(zp - mu[u]), dn = fabsf(zn - mu[u]);
-                            path_wins = dp < dn || (dp == dn && zp <= zn);
-                        } else {
-                            path_wins = use_r ? zp >= zn : zp <= zn;
-                        }
-                        const int i = path_wins ? ipn : inb;
-                        const float zh = path_wins ? zp : zn;
-                        const int q = ((2 * i + 1) << (N - n)) - 1;
-                        if (ok[u]) {
-                            const size_t o = lam_off + off + u * off_step + cc;
-                            if (a.em) eb = __ldg(a.em + ((size_t)lam * C + cc) * a.Q + q);
-                            if (a.zhat) a.zhat[o] = zh;
-                            if (a.qidx) a.qidx[o] = q;
-                            if (a.level) a.level[o] = n;
-                            if (a.bits) a.bits[o] = ln;
-                            if (a.em_bits) a.em_bits[o] = eb;
+                    for (int j = 0; j < LP; ++j) {
+                        const float npn = pl[j][n * VBQ_GROUP];
+                        const float2 sl = __fadd2_rn(hL[n], make_float2(npn, npn));
+                        if (sl.x > bL[j][0]) { bL[j][0] = sl.x; nL[j][0] = n; }
+                        if (sl.y > bL[j][1]) { bL[j][1] = sl.y; nL[j][1] = n; }
+                        if (!FAST) {
+                            const float2 sr = __fadd2_rn(hR[n], make_float2(npn, npn));
+                            if (sr.x > bR[j][0]) { bR[j][0] = sr.x; nR[j][0] = n; }
+                            if (sr.y > bR[j][1]) { bR[j][1] = sr.y; nR[j][1] = n; }
                         }
                     }
-                    if (TOTALS && ok[u]) {
-                        // distortion of the winner = -(h) = pen - (-score) up to one float32 rounding of the score
-                        const float npw = pl[n * VBQ_GROUP];
-                        t_level += n;
-                        t_len += (double)ln;
-                        t_em += (double)eb;
-                        t_dist += (double)npw - (double)best;
-                    }
                 }
-                if (TOTALS) {
-                    t_level = __reduce_add_sync(0xffffffffu, t_level);
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        t_len += __shfl_xor_sync(0xffffffffu, t_len, o);
-                        t_em += __shfl_xor_sync(0xffffffffu, t_em, o);
-                        t_dist += __shfl_xor_sync(0xffffffffu, t_dist, o);
+                for (int j = 0; j < LP; ++j) {
+                    const int lam = lam0 + j;
+                    if (lam >= L) break;
+                    double t_len = 0.0, t_em = 0.0, t_dist = 0.0;
+                    int t_level = 0;
+                    const size_t lam_off = (size_t)lam * (size_t)a.lam_stride;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const bool use_r = !FAST && (bR[j][u] > bL[j][u]);
+                        const int n = use_r ? nR[j][u] : nL[j][u];
+                        const float best = use_r ? bR[j][u] : bL[j][u];
+                        const float ln = a.len ? sLen[((size_t)lam * (N + 1) + n) * VBQ_GROUP + col] : (float)n;
+                        float eb = 0.0f;
+                        if (any_out || a.em) {
+                            // rebuild the bracket of depth n from the final path (see quantize.cu)
+                            const int sh = N + 1 - n;
+                            const int ipn = idx[u] >> sh;
+                            const int d = ((idx[u] >> (sh - 1)) & 1) ? 1 : -1;
+                            const int last = (1 << n) - 1;
+                            int inb = min(max(ipn + d, 0), last);
+                            if (n == N && ipn + d > last) inb = max(last - 1, 0);
+                            const float *e = sTc + (entry_of(n, 0) + ipn) * VBQ_GROUP;
+                            const float zp = e[0], zn = e[d * VBQ_GROUP];
+                            bool path_wins;
+                            if (FAST) {
+                                const float dp = fabsf(zp - mu[u]), dn = fabsf(zn - mu[u]);
+                                path_wins = dp < dn || (dp == dn && zp <= zn);
+                            } else {
+                                path_wins = use_r ? zp >= zn : zp <= zn;
+                            }
+                            const int i = path_wins ? ipn : inb;
+                            const float zh = path_wins ? zp : zn;
+                            const int q = ((2 * i + 1) << (N - n)) - 1;
+                            if (ok[u]) {
+                                const size_t o = lam_off + off + u * off_step + cc;
+                                if (a.em) eb = __ldg(a.em + ((size_t)lam * C + cc) * a.Q + q);
+                                if (a.zhat) a.zhat[o] = zh;
+                                if (a.qidx) a.qidx[o] = q;
+                                if (a.level) a.level[o] = n;
+                                if (a.bits) a.bits[o] = ln;
+                                if (a.em_bits) a.em_bits[o] = eb;
+                            }
+                        }
+                        if (TOTALS && ok[u]) {
+                            // distortion of the winner = -h = pen - (-score), up to one float32 rounding of the score
+                            const float npw = pl[j][n * VBQ_GROUP];
+                            t_level += n;
+                            t_len += (double)ln;
+                            t_em += (double)eb;
+                            t_dist += (double)npw - (double)best;
+                        }
                     }
-                    if (lane == 0) {
-                        double *acc = sAcc + ((size_t)warp * L + lam) * VBQ_TOTALS;
-                        acc[0] += (double)t_level;
-                        acc[1] += t_len;
-                        acc[2] += t_em;
-                        acc[3] += t_dist;
+                    if (TOTALS) {
+                        t_level = __reduce_add_sync(0xffffffffu, t_level);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            t_len += __shfl_xor_sync(0xffffffffu, t_len, o);
+                            t_em += __shfl_xor_sync(0xffffffffu, t_em, o);
+                            t_dist += __shfl_xor_sync(0xffffffffu, t_dist, o);
+                        }
+                        if (lane == 0) {
+                            double *acc = sAcc + ((size_t)warp * L + lam) * VBQ_TOTALS;
+                            acc[0] += (double)t_level;
+                            acc[1] += t_len;
+                            acc[2] += t_em;
+                            acc[3] += t_dist;
+                        }
                     }
                 }
             }
@@ -283,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_sweep_kernel(const QArgs a) {
     }
 }
 
-template <bool FAST, bool TOTALS, int T>
+template <bool FAST, bool TOTALS, int T, int LP>
 static int launch_sweep_t(QArgs a, int sms, cudaStream_t st) {
     constexpr int U = 2;
     constexpr int rows_per_pass = T / VBQ_GROUP;
@@ -295,11 +308,11 @@ static int launch_sweep_t(QArgs a, int sms, cudaStream_t st) {
     // shared memory: tree + staging ring are fixed, penalties / lengths / accumulators grow with the lambda count;
     // calls with more lambdas than fit are served in lambda chunks
     const size_t fixed = ((size_t)kPadEntries * VBQ_GROUP + (size_t)kStages * 2 * U * T) * sizeof(float);
-    const size_t per_lambda = 2 * (size_t)(a.N + 1) * VBQ_GROUP * sizeof(float) +
+    const size_t per_lambda = (a.len ? 2 : 1) * (size_t)(a.N + 1) * VBQ_GROUP * sizeof(float) +
                               (TOTALS ? (size_t)(T / 32) * VBQ_TOTALS * sizeof(double) : 0);
     const int max_l = (int)((227 * 1024 - fixed) / per_lambda);
     if (max_l < 2) return -1;
-    auto kern = vbq_sweep_kernel<FAST, TOTALS, T>;
+    auto kern = vbq_sweep_kernel<FAST, TOTALS, T, LP>;
     const int n_lambda = a.n_lambda;
     const size_t pen_stride = (size_t)a.pen_channels * (a.N + 1);
     for (int l0 = 0; l0 < n_lambda; l0 += max_l) {
@@ -330,7 +343,19 @@ static int launch_sweep_t(QArgs a, int sms, cudaStream_t st) {
 int vbq_launch_sweep(const QArgs &a, int sms, cudaStream_t st) {
     if (a.N > kSmemDepth || a.n_lambda < 2) return -1;
     const bool fast = (a.flags & VBQ_FLAG_FAST) != 0, tot = a.totals != nullptr;
-    constexpr int T = 256;
-    if (fast) return tot ? launch_sweep_t<true, true, T>(a, sms, st) : launch_sweep_t<true, false, T>(a, sms, st);
-    return tot ? launch_sweep_t<false, true, T>(a, sms, st) : launch_sweep_t<false, false, T>(a, sms, st);
+    int tune = 41;   // development override: VBQ_SWEEP_TUNE=<threads/128><lambdas per group>
+    if (const char *e = getenv("VBQ_SWEEP_TUNE")) tune = atoi(e);
+#define SWEEP_CASE(T, LP)                                                                                        \
+    if (fast) return tot ? launch_sweep_t<true, true, T, LP>(a, sms, st) : launch_sweep_t<true, false, T, LP>(a, sms, st); \
+    return tot ? launch_sweep_t<false, true, T, LP>(a, sms, st) : launch_sweep_t<false, false, T, LP>(a, sms, st);
+    switch (tune) {
+        case 21: { SWEEP_CASE(256, 1) }
+        case 24: { SWEEP_CASE(256, 4) }
+        case 42: { SWEEP_CASE(512, 2) }
+        case 32: { SWEEP_CASE(384, 2) }
+        case 22: { SWEEP_CASE(256, 2) }
+        case 51: { SWEEP_CASE(640, 1) }
+        default: { SWEEP_CASE(512, 1) }
+    }
+#undef SWEEP_CASE
 }
