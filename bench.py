@@ -250,15 +250,28 @@ def run_ours(args, rank, world, local_rank):
         sets.append(dict(mu=mu, sigma=sigma,
                          qidx=torch.empty((1, ROWS, C), dtype=torch.int32, device=dev),
                          bits=torch.empty((1, ROWS, C), dtype=torch.float32, device=dev)))
-    totals = torch.zeros((1, 4), dtype=torch.float64, device=dev)
+    # per-step totals live in a small ring so that the NCCL all-reduce of step i (asynchronous, on NCCL's own
+    # stream) overlaps the kernel of step i+1; all pending reductions are waited for inside the timed region
+    n_ring = 8
+    totals_ring = [torch.zeros((1, 4), dtype=torch.float64, device=dev) for _ in range(n_ring)]
+    totals = totals_ring[0]
     ws = ops.quantize_workspace(1, dev)
+    pending = []
 
     def step(i):
         b = sets[i % n_sets]
+        t = totals_ring[i % n_ring]
+        if world > 1 and len(pending) >= n_ring - 1:
+            pending.pop(0).wait()
         ops.quantize_into(b["mu"], b["sigma"], q.all_code_points, q._packed, pen, length, None, N_BITS,
-                          qidx=b["qidx"], bits=b["bits"], totals=totals, workspace=ws, flags=args.flags)
+                          qidx=b["qidx"], bits=b["bits"], totals=t, workspace=ws, flags=args.flags)
         if world > 1:
-            sharding.all_reduce_totals(totals)
+            pending.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True))
+        return t
+
+    def drain():
+        while pending:
+            pending.pop(0).wait()
 
     def barrier():
         if world > 1:
@@ -267,6 +280,7 @@ def run_ours(args, rank, world, local_rank):
 
     for i in range(args.warmup):
         step(i)
+    drain()
     barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     with ClockSampler(local_rank) as clocks:
@@ -275,6 +289,7 @@ def run_ours(args, rank, world, local_rank):
         for i in range(args.steps):
             step(args.warmup + i)
             ev[i + 1].record()
+        drain()
         barrier()
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
@@ -308,6 +323,7 @@ def run_ours(args, rank, world, local_rank):
         e2e_step(i)
     # the pipeline must reproduce the device-resident results exactly
     step(0)
+    drain()
     torch.cuda.synchronize()
     pipe.run(h_mu[0], h_sigma[0], q.all_code_points, q._packed, pen, length, None, qidx=h_q, bits=h_b, totals=h_tot,
              flags=args.flags)

@@ -143,6 +143,33 @@ int vbq_quantize_host(vbq_host_ctx *ctx, const float *h_mu, const float *h_sigma
                       float *h_zhat, int *h_qidx, int *h_level, float *h_bits, float *h_em_bits, double *h_totals,
                       unsigned flags);
 
+/* ---- word embeddings: the notebook's float64 search (ipynb:429-443) ------------------------------------------- */
+
+/* compress_coordinates for one shared prior: d_mu, d_sigma (n) float32, d_codepoints (Q) float64 heap order
+ * (ipynb:383-390), d_lengths (N+1) float64 code length of each bit depth, N <= 12.  Minimises
+ * (c-mu)^2 + (2 beta) sigma^2 len(c) with the notebook's float64 roundings, first minimum in heap order.
+ * pen_f32 != 0: (2 beta) sigma^2 is formed in float32 first (NumPy 1.17, or a Python-float beta under NumPy 2).
+ * Outputs (n), any may be NULL: the optimum cast to float32, its heap index, its bit depth. */
+int vbq_compress_coordinates_f64(const float *d_mu, const float *d_sigma, long long n, const double *d_codepoints,
+                                 int N, const double *d_lengths, double beta, int pen_f32, float *d_optima,
+                                 int *d_heap_index, int *d_level, void *stream);
+
+/* ---- stand-alone operator forms ------------------------------------------------------------------------------- */
+
+/* ChannelwisePriorCDFQuantizer.get_all_N_bit_intervals (quantizer.py:65-80): d_mu (rows, C) -> d_left, d_right
+ * (C, N+1, rows): at every bit depth the largest code point below mu and the smallest one >= mu, with the edge
+ * semantics of the reference's padded search grids. */
+int vbq_intervals(const float *d_mu, long long rows, int C, const float *d_table, int N, float *d_left,
+                  float *d_right, void *stream);
+
+/* utils.batch_quantize_indep_dims (utils.py:363-423) on explicit candidates: d_P (M, BK) float32 code points,
+ * d_L (M, BK) or (n_lambda, M, BK) code lengths (int32, or float32 when l_is_float), scores
+ * fun_P - fl(lambda*L) with fun_P = d_funP (M, BK) if given, else -0.5*((P-loc)/scale)^2 (utils.py:318-320) from
+ * d_loc, d_scale (BK).  Outputs (n_lambda, BK): chosen code point, its code length (dtype of d_L), optional index. */
+int vbq_argmax_candidates(const float *d_P, const void *d_L, int l_is_float, int l_per_lambda, const float *d_funP,
+                          const float *d_loc, const float *d_scale, const float *d_lambs, int n_lambda, int M,
+                          long long BK, float *d_zhat, void *d_bits, int *d_index, void *stream);
+
 /* Self-test helper: out[i] = the kernel's division a[i]/b[i] (reciprocal + FMA correction) so that tests can
  * compare it with IEEE division bit for bit. */
 int vbq_selftest_divide(const float *d_a, const float *d_b, long long n, float *d_out, void *stream);

@@ -231,12 +231,15 @@ def compress_coordinates(means, stds, beta, codepoints, bitlengths, chunk=100000
     return optima, idxs.reshape(means.shape)
 
 
-def compress_coordinates_bracket(means, stds, beta, codepoints, N):
+def compress_coordinates_bracket(means, stds, beta, codepoints, N, pen_f64=False):
     """Same objective and tie rule (first minimum in heap order) as ``compress_coordinates`` but evaluated only
     on the 2N+1 bracketing candidates (equivalence claimed at ipynb:482).  float64."""
     beta = float(beta)
     m = means.ravel().astype(np.float64)
-    pen_unit = ((2 * beta) * stds.ravel() ** 2).astype(np.float64)  # float32 product promoted afterwards
+    if pen_f64:   # NumPy >= 2 with a NumPy float64 `beta`: the product is formed in float64 (SURVEY §7.3-7)
+        pen_unit = (2 * beta) * (stds.ravel() ** 2).astype(np.float64)
+    else:
+        pen_unit = ((2 * beta) * stds.ravel() ** 2).astype(np.float64)  # float32 product promoted afterwards
     best = np.full(m.shape, np.inf)
     best_h = np.zeros(m.shape, dtype=np.int64)
     for n in range(N + 1):

@@ -136,21 +136,71 @@ def test_embedding_path_against_notebook():
     # norm.ppf on the device in float64 vs SciPy
     assert np.max(np.abs(cb.codepoints - g["codepoints"]) / np.abs(g["codepoints"]).clip(1e-3)) < 1e-11
     assert np.array_equal(cb.lengths, g["lengths"])
+    cb.codepoints = g["codepoints"].copy()      # same table on both sides for the search test below
     tot = mism = 0
     for i, beta in enumerate(g["betas"]):
+        want = g["optima_%d" % i]
+        # float64 kernel: the notebook's arithmetic, bit for bit
         optima, none = cb.compress_coordinates(g["means"], g["stds"], float(beta))
         assert none is None and optima.dtype == np.float32 and optima.shape == g["means"].shape
-        want = g["optima_%d" % i]
-        bad = optima != want
-        # every chosen value is a (float32-rounded) code point; disagreements with the notebook's float64 search are
-        # near-ties: the alternative's float64 loss must be within 1e-5 relative of the notebook's optimum
+        assert np.array_equal(optima, want), "beta=%g: %d differ" % (beta, (optima != want).sum())
+        # float32 image-path kernel on the same problem: only near-ties may differ
+        fast, _ = cb.compress_coordinates(g["means"], g["stds"], float(beta), exact=False)
+        bad = fast != want
         if bad.any():
             m, s = g["means"][bad].astype(np.float64), g["stds"][bad].astype(np.float64)
             pen = lambda z: np.array([g["lengths"][np.argmin(np.abs(g["codepoints"] - v))] for v in z])  # noqa: E731
             loss = lambda z: (z - m) ** 2 + 2 * float(beta) * s ** 2 * pen(z)                            # noqa: E731
-            la, lb = loss(optima[bad].astype(np.float64)), loss(want[bad].astype(np.float64))
+            la, lb = loss(fast[bad].astype(np.float64)), loss(want[bad].astype(np.float64))
             assert np.all(np.abs(la - lb) <= 1e-5 * np.abs(lb) + 1e-12)
         tot += bad.size
         mism += int(bad.sum())
-    print("embeddings: %d of %d optima differ from the float64 notebook search (near-ties)" % (mism, tot))
+    print("embeddings, float32 kernel: %d of %d optima differ from the float64 notebook search (near-ties)" % (mism, tot))
     assert mism <= tot // 20000 + 3
+
+
+def test_embedding_f64_kernel_vs_oracle_large():
+    """1.5 M coordinates (SURVEY §8d C1 statistics at half size): float64 kernel == exhaustive notebook restatement."""
+    import vbq_b200
+    from oracle import vbq_oracle as O
+    rng = np.random.default_rng(11)
+    means = rng.normal(-0.08, 1.2329, (15000, 100)).astype(np.float32)
+    stds = np.exp(rng.normal(np.log(0.04), 0.7, means.shape)).astype(np.float32)
+    cb = vbq_b200.GaussianCodebook(vbq_b200.word_embeddings.empirical_std(means), 10)
+    for beta in (1.0, np.float64(37.5)):
+        got, _ = cb.compress_coordinates(means, stds, beta)
+        want, _ = O.compress_coordinates_bracket(means, stds, beta, cb.codepoints, 10,
+                                                 pen_f64=isinstance(beta, np.floating))
+        assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("name", LEARNED)
+def test_intervals_equal_reference(name):
+    g = load(name)
+    q = make_quantizer(g)
+    left, right = q.get_all_N_bit_intervals(g["means"].reshape(-1, int(g["C"])))
+    assert np.array_equal(left.cpu().numpy(), g["left"]) and np.array_equal(right.cpu().numpy(), g["right"])
+
+
+def test_generic_operator_equals_reference():
+    """utils.batch_quantize_indep_dims (3-D candidates, int32 lengths, Gaussian fun) vs the reference's NumPy run."""
+    from vbq_b200 import utils
+    g = load("utils_numpy")
+    lambs = [float(l) for l in g["bq_lambs"]]
+    B, K = g["bq_loc"].shape
+    fun = utils.curry_normal_logpdf(loc=g["bq_loc"], scale=g["bq_scale"], ignore_const=True)
+    Zh, nb = utils.batch_quantize_indep_dims((B, K), g["bq_P"], g["bq_L"], fun, lambs)
+    for i, l in enumerate(lambs):
+        assert np.array_equal(Zh[l], g["bq_zhat_%d" % i])
+        assert nb[l].dtype == np.int32 and np.array_equal(nb[l], g["bq_bits_%d" % i])
+    # arbitrary callable `fun` (evaluated by the caller on device tensors) + 2-D (K, M) candidates
+    P2 = np.sort(np.random.default_rng(0).normal(0, 2, (K, 7)).astype(np.float32), axis=1)
+    L2 = np.tile(np.arange(7, dtype=np.int32), (K, 1))
+    loc = torch.from_numpy(g["bq_loc"]).cuda()
+    Zh2, nb2 = utils.batch_quantize_indep_dims((B, K), P2, L2, lambda z: -torch.abs(z - loc), [0.3])
+    Pb = np.repeat(P2.T[:, None, :], B, axis=1)
+    Lb = np.repeat(L2.T[:, None, :], B, axis=1)
+    s = -np.abs(Pb - g["bq_loc"]) - np.float32(0.3) * Lb.astype(np.float32)
+    k = np.argmax(s, axis=0)
+    assert np.array_equal(Zh2[0.3], np.take_along_axis(Pb, k[None], 0)[0])
+    assert np.array_equal(nb2[0.3], np.take_along_axis(Lb, k[None], 0)[0])

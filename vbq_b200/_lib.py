@@ -50,6 +50,9 @@ SIGNATURES = {
     "vbq_host_ctx_create": (_i, [_i, _i, _i, _ll, _u, C.POINTER(C.c_void_p)]),
     "vbq_host_ctx_destroy": (_i, [_p]),
     "vbq_quantize_host": (_i, [_p, _p, _p, _ll, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _u]),
+    "vbq_compress_coordinates_f64": (_i, [_p, _p, _ll, _p, _i, _p, C.c_double, _i, _p, _p, _p, _p]),
+    "vbq_intervals": (_i, [_p, _ll, _i, _p, _i, _p, _p, _p]),
+    "vbq_argmax_candidates": (_i, [_p, _p, _i, _i, _p, _p, _p, _p, _i, _i, _ll, _p, _p, _p, _p]),
     "vbq_selftest_divide": (_i, [_p, _p, _ll, _p, _p]),
 }
 

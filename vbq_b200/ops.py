@@ -344,3 +344,77 @@ class HostPipeline:
             self.close()
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------------------------------------------
+# stand-alone operator forms
+# ------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("vbq::intervals", mutates_args=())
+def intervals(mu: torch.Tensor, table: torch.Tensor, max_bits: int) -> List[torch.Tensor]:
+    """get_all_N_bit_intervals (quantizer.py:65-80): mu (B, C) -> [left, right], each (C, N+1, B)."""
+    _need_cuda("mu", mu, torch.float32, 2)
+    _need_cuda("table", table, torch.float32, 2)
+    rows, C = mu.shape
+    if tuple(table.shape) != (C, num_levels(max_bits)):
+        raise ValueError("vbq_b200: table must be (C, Q)")
+    left = torch.empty((C, max_bits + 1, rows), dtype=torch.float32, device=mu.device)
+    right = torch.empty_like(left)
+    st = _lib.load().vbq_intervals(_ptr(mu), rows, C, _ptr(table), max_bits, _ptr(left), _ptr(right),
+                                   _stream(mu.device))
+    _lib.check(st, "vbq_intervals")
+    return [left, right]
+
+
+@intervals.register_fake
+def _(mu, table, max_bits):
+    rows, C = mu.shape
+    e = mu.new_empty((C, max_bits + 1, rows))
+    return [e, e.clone()]
+
+
+def argmax_candidates(P, L, lambs, fun_P=None, loc=None, scale=None):
+    """utils.batch_quantize_indep_dims on device tensors: P (M, B, K) float32, L (M, B, K) or (Lambda, M, B, K)
+    int32/float32, and either fun_P (M, B, K) or loc/scale (B, K).  Returns (zhat (Lambda,B,K), bits, index)."""
+    _need_cuda("P", P, torch.float32, 3)
+    M, B, K = P.shape
+    if L.dtype not in (torch.int32, torch.float32):
+        raise TypeError("vbq_b200: code lengths must be int32 or float32")
+    _need_cuda("L", L, L.dtype)
+    per_lambda = L.dim() == 4
+    n_lambda = len(lambs)
+    if tuple(L.shape) != (((n_lambda,) if per_lambda else ()) + (M, B, K)):
+        raise ValueError("vbq_b200: L must be (M,B,K) or (n_lambda,M,B,K)")
+    lam = torch.tensor([float(l) for l in lambs], dtype=torch.float32, device=P.device)
+    if fun_P is not None:
+        _need_cuda("fun_P", fun_P, torch.float32, 3)
+    else:
+        _need_cuda("loc", loc, torch.float32, 2)
+        _need_cuda("scale", scale, torch.float32, 2)
+    zhat = torch.empty((n_lambda, B, K), dtype=torch.float32, device=P.device)
+    bits = torch.empty((n_lambda, B, K), dtype=L.dtype, device=P.device)
+    index = torch.empty((n_lambda, B, K), dtype=torch.int32, device=P.device)
+    st = _lib.load().vbq_argmax_candidates(_ptr(P), _ptr(L), int(L.dtype == torch.float32), int(per_lambda),
+                                           _ptr(fun_P), _ptr(loc), _ptr(scale), _ptr(lam), n_lambda, M, B * K,
+                                           _ptr(zhat), _ptr(bits), _ptr(index), _stream(P.device))
+    _lib.check(st, "vbq_argmax_candidates")
+    return zhat, bits, index
+
+
+def compress_coordinates_f64(mu, sigma, codepoints, lengths, beta, pen_f32=True, want_index=False, want_level=False):
+    """The notebook's float64 search (vbq_compress_coordinates_f64): mu, sigma float32 CUDA tensors of equal shape,
+    codepoints (Q,) float64 heap order, lengths (N+1,) float64.  Returns (optima float32, heap index, level)."""
+    _need_cuda("mu", mu, torch.float32)
+    _need_cuda("sigma", sigma, torch.float32)
+    _need_cuda("codepoints", codepoints, torch.float64, 1)
+    _need_cuda("lengths", lengths, torch.float64, 1)
+    N = lengths.numel() - 1
+    if codepoints.numel() != num_levels(N) or mu.shape != sigma.shape:
+        raise ValueError("vbq_b200: codepoints must have 2^(N+1)-1 entries and mu/sigma equal shapes")
+    optima = torch.empty_like(mu)
+    index = torch.empty(mu.shape, dtype=torch.int32, device=mu.device) if want_index else None
+    level = torch.empty(mu.shape, dtype=torch.int32, device=mu.device) if want_level else None
+    st = _lib.load().vbq_compress_coordinates_f64(_ptr(mu), _ptr(sigma), mu.numel(), _ptr(codepoints), N,
+                                                  _ptr(lengths), float(beta), int(bool(pen_f32)), _ptr(optima),
+                                                  _ptr(index), _ptr(level), _stream(mu.device))
+    _lib.check(st, "vbq_compress_coordinates_f64")
+    return optima, index, level

@@ -64,6 +64,14 @@ class ChannelwisePriorCDFQuantizer:
         return [[self.all_code_points[c, 2 ** n - 1: 2 ** (n + 1) - 1] for n in range(N + 1)]
                 for c in range(self.num_channels)]
 
+    def get_all_N_bit_intervals(self, Z):
+        """Reference quantizer.py:65-80: Z (B, C) -> (left_endpoints, right_endpoints), each (C, N+1, B): the code
+        points of every bit depth that bracket Z (device tensors)."""
+        assert self.all_code_points is not None, "call build_code_points first"
+        z = utils.as_device_f32(Z, self.device).reshape(-1, self.num_channels).contiguous()
+        left, right = ops.intervals(z, self.all_code_points, self.max_bits_per_coord)
+        return left, right
+
     # ------------------------------------------------------------------------------------------------
     # code lengths / penalties (reference quantizer.py:166-180, utils.py:388-396)
     # ------------------------------------------------------------------------------------------------

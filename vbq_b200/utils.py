@@ -50,3 +50,46 @@ def as_device_f32(x, device):
 def lambda_key_list(lambs):
     """The reference keys its dicts by the lambda objects themselves (quantizer.py:172,226)."""
     return list(lambs)
+
+
+def batch_quantize_indep_dims(Z_shape, code_points, code_lengths, fun, lambs, backend=None, return_np=True,
+                              device="cuda"):
+    """Reference utils.py:363-423: for every batch element and dimension pick the candidate maximising
+    fun(P) - lamb * L, first maximum, for every lamb.  ``code_points`` / ``code_lengths`` are (K, M) or (M, B, K)
+    (lengths may also be (Lambda, M, B, K)).  Runs on the GPU (`vbq_argmax_candidates`); ``backend`` is accepted for
+    signature compatibility and ignored.  ``fun`` may be the object returned by `curry_normal_logpdf` (then the
+    float32 Gaussian score is computed inside the kernel) or any callable on torch tensors."""
+    from . import ops
+    B, K = Z_shape
+    dev = torch.device(device)
+
+    def to_dev(x, dtype=None):
+        t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(x))
+        if dtype is None:
+            dtype = torch.float32 if t.dtype.is_floating_point else torch.int32
+        return t.to(device=dev, dtype=dtype)
+
+    P = to_dev(code_points, torch.float32)
+    L = to_dev(code_lengths)
+    if P.dim() == 2:                                             # (K, M) -> (M, B, K), utils.py:385-386
+        P = P.t()[:, None, :].expand(-1, B, -1)
+        L = L.t()[:, None, :].expand(-1, B, -1)
+    else:
+        assert P.dim() == 3
+    P, L = P.contiguous(), L.contiguous()
+    if isinstance(fun, NormalLogpdf) and fun.ignore_const:
+        loc = to_dev(fun.loc, torch.float32).expand(B, K).contiguous()
+        scale = to_dev(fun.scale, torch.float32).expand(B, K).contiguous()
+        zhat, bits, _ = ops.argmax_candidates(P, L, lambs, loc=loc, scale=scale)
+    else:
+        fun_P = fun(P)
+        fun_P = to_dev(fun_P, torch.float32).contiguous()
+        zhat, bits, _ = ops.argmax_candidates(P, L, lambs, fun_P=fun_P)
+    Z_hat_dict, num_bits_dict = {}, {}
+    for i, lamb in enumerate(lambs):
+        z, nb = zhat[i], bits[i]
+        if return_np:
+            z, nb = z.cpu().numpy(), nb.cpu().numpy()
+        Z_hat_dict[lamb] = z
+        num_bits_dict[lamb] = nb
+    return Z_hat_dict, num_bits_dict

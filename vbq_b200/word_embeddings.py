@@ -70,16 +70,27 @@ class GaussianCodebook:
 
         return dict(zhat=unpad(z), qidx=unpad(q), level=unpad(lv), bits=unpad(b), totals=tot)
 
-    def compress_coordinates(self, means, stds, beta, bitlengths=None):
+    def compress_coordinates(self, means, stds, beta, bitlengths=None, exact=True):
         """Notebook signature (ipynb:429-443): returns (optima shaped and typed like `means`, None).
-        Minimises (c - mu)^2 + 2 beta sigma^2 len(c) over the code points, i.e. lambda = beta in
-        -0.5((c-mu)/sigma)^2 - lambda len."""
+        Minimises (c - mu)^2 + 2 beta sigma^2 len(c) over the code points.
+
+        ``exact=True`` (default) runs the float64 kernel that reproduces the notebook's arithmetic bit for bit
+        (float64 code points and losses; `(2*beta)*stds**2` in float32 unless `beta` is a NumPy float64 scalar, which
+        NumPy >= 2 promotes to float64).  ``exact=False`` runs the float32 image-path kernel (lambda = beta), which
+        is faster and differs only on near-ties."""
         is_np = not isinstance(means, torch.Tensor)
         m = torch.as_tensor(np.asarray(means)) if is_np else means
         s = torch.as_tensor(np.asarray(stds)) if is_np else stds
         m32 = m.to(device=self.device, dtype=torch.float32).contiguous()
         s32 = s.to(device=self.device, dtype=torch.float32).contiguous()
-        out = self.quantize(m32, s32, [beta], bitlengths)['zhat'][0]
+        if exact:
+            per_level = self._level_lengths(self.lengths if bitlengths is None else bitlengths)
+            pen_f32 = not (isinstance(beta, np.floating) and np.lib.NumpyVersion(np.__version__) >= "2.0.0")
+            out, _, _ = ops.compress_coordinates_f64(
+                m32, s32, torch.from_numpy(self.codepoints).to(self.device),
+                torch.from_numpy(per_level.astype(np.float64)).to(self.device), float(beta), pen_f32)
+        else:
+            out = self.quantize(m32, s32, [beta], bitlengths)['zhat'][0]
         if is_np:
             return out.cpu().numpy().astype(np.asarray(means).dtype), None
         return out.to(means.dtype), None
