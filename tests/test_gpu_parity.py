@@ -212,3 +212,52 @@ def test_sweep_equals_per_lambda_walks(N, C, rows, n_lambda, corrected, fast):
         assert torch.equal(a[k], b[k]), k
     assert torch.allclose(a["totals"], b["totals"], rtol=1e-6, atol=1e-9)
     assert torch.equal(a["totals"][:, :3], b["totals"][:, :3])     # integer / float sums of identical terms
+
+
+def test_strict_mode_equals_reference_walk():
+    """Default mode (nearer bracket end + exact tie fallback) vs VBQ_FLAG_REFERENCE_WALK (both ends, two running
+    maxima) on 3.1 M coordinates: identical outputs for every lambda."""
+    import vbq_b200
+    from vbq_b200 import ops
+    C, N, rows = 48, 10, 65536
+    pr = H.make_prior(C, seed=77)
+    q = vbq_b200.ChannelwisePriorCDFQuantizer(C, N)
+    q.set_code_points(ops.build_code_points_learned(_dev(pr.packed()), N))
+    rng = np.random.default_rng(5)
+    srt = q.code_points_by_channel.cpu().numpy()
+    idx = rng.integers(0, srt.shape[1], (rows, C))
+    mu = (srt[np.arange(C)[None, :], idx] + rng.normal(0, 0.05, (rows, C))).astype(np.float32)
+    sigma = np.exp(0.5 * rng.normal(-3, 1.5, (rows, C))).astype(np.float32)
+    outs = ops.OUT_ZHAT | ops.OUT_QIDX | ops.OUT_LEVEL
+    for lamb in (0.0, 2.0 ** -8, 0.5, 16.0):
+        for extra in (0, ops.FLAG_NO_PRUNE):
+            a = q.quantize(_dev(mu), _dev(sigma), [lamb], outputs=outs, flags=extra)
+            b = q.quantize(_dev(mu), _dev(sigma), [lamb], outputs=outs, flags=extra | ops.FLAG_REFERENCE_WALK)
+            for k in ("zhat", "qidx", "level"):
+                assert torch.equal(a[k], b[k]), (lamb, extra, k)
+
+
+@pytest.mark.parametrize("flags", [0, 2, 32])
+def test_massive_ties_follow_argmax_order(flags):
+    """sigma so large that every distortion term underflows to zero: with lambda = 0 all 2N+1 candidates tie and the
+    reference's argmax returns candidate 0 (left_0); with lambda > 0 depth 0 wins outright.  Exercises the tie
+    fallback of the default mode."""
+    import vbq_b200
+    from vbq_b200 import ops
+    C, N, rows = 16, 10, 256
+    pr = H.make_prior(C, seed=8)
+    q = vbq_b200.ChannelwisePriorCDFQuantizer(C, N)
+    q.set_code_points(ops.build_code_points_learned(_dev(pr.packed()), N))
+    table = q.all_code_points.cpu().numpy()
+    mu, _, _ = H.make_latents(pr, rows, 3, table=table)
+    sigma = np.full_like(mu, 1e30)
+    sigma[::2] = np.float32(3e19)          # t^2 ~ 1e-37: deep in the subnormal range, many equal scores
+    oq = O.QuantizerNP(C, N)
+    oq.set_code_points(table)
+    lambs = [0.0, 1e-30, 0.5]
+    out = q.quantize(_dev(mu), _dev(sigma), lambs, flags=flags | ops.FLAG_NO_SWEEP,
+                     outputs=ops.OUT_ZHAT | ops.OUT_LEVEL)
+    Zo, Bo = oq.compress_batch_channel_latents(mu, sigma, lambs)
+    for i, l in enumerate(lambs):
+        assert np.array_equal(out["zhat"][i].cpu().numpy(), Zo[l]), l
+        assert np.array_equal(out["level"][i].cpu().numpy(), Bo[l]), l

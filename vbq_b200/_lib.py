@@ -15,6 +15,7 @@ FLAG_NO_PRUNE = 2
 FLAG_FAST = 4
 FLAG_ACCUMULATE_TOTALS = 8
 FLAG_NO_SWEEP = 16
+FLAG_REFERENCE_WALK = 32
 GROUP = 16
 TOTALS = 4
 PRIOR_PARAMS = 43

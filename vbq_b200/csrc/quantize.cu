@@ -52,8 +52,45 @@ __global__ void pack_table_kernel(const float *__restrict__ table, int C, int N,
 }
 
 
-template <bool FAST, bool PRUNE, bool TOTALS, bool DEEP, int U, int kThreads>
+// Scoring modes.  All three produce the reference's result; they differ in how much work proves it.
+//   kModeReference: both bracket ends of every depth are scored with the reference's float32 roundings and two
+//                   running maxima (left / right candidates) reproduce argmax's first-maximum order directly.
+//   kModeStrict   : (default) only the NEARER end of every depth is scored (same roundings; the farther end can never
+//                   score higher), one running maximum; the left/right decision is made exactly for the winning depth
+//                   in the epilogue, and whenever two depths reach exactly the same float32 score (the only situation
+//                   in which the candidate order matters) the coordinate is re-done by `reference_walk`.
+//                   Bit-identical to kModeReference by construction and by test.
+//   kModeFast     : nearer end, d*d*(0.5/sigma^2) instead of the division; may differ inside float32 rounding ties.
+constexpr int kModeReference = 0, kModeStrict = 1, kModeFast = 2;
+
+// Fully faithful scalar walk of one coordinate (the slow path of kModeStrict): returns the winning depth and side.
+__device__ __noinline__ int reference_walk(const char *pb, const float *sPenc, float z0, float mu, float sg, int NS) {
+    const float rs = __frcp_rn(sg);
+    float bestL = score_exact(z0, mu, sg, rs, sPenc[0]), bestR = -CUDART_INF_F;
+    int nL = 0, nR = 0;
+    int V = mu > z0 ? 96 : 32;
+    for (int n = 1; n <= NS; ++n) {
+        const int imm = entry_of(n, 0) * kRowStrideBytes;
+        const char *pa = pb + V;
+        const float zp = lds_f32(pa, imm);
+        const int s = mu > zp ? 32 : -32;
+        const float zn = lds_f32(pa + 2 * s, imm);
+        V = 2 * V + s;
+        const float npn = sPenc[n * VBQ_GROUP];
+        const float sl = score_exact(fminf(zp, zn), mu, sg, rs, npn);
+        const float sr = score_exact(fmaxf(zp, zn), mu, sg, rs, npn);
+        if (sl > bestL) { bestL = sl; nL = n; }
+        if (sr > bestR) { bestR = sr; nR = n; }
+    }
+    return bestR > bestL ? (nR | 0x100) : nL;
+}
+
+// NT > 0: max_bits_per_coord == NT is known at compile time (no per-depth bound checks); NT == 0: runtime depth.
+template <int MODE, bool PRUNE, bool TOTALS, bool DEEP, int NT, int U, int kThreads>
 __global__ void __launch_bounds__(kThreads, 1) vbq_quantize_kernel(const QArgs a) {
+    constexpr bool FAST = MODE == kModeFast;
+    constexpr bool STRICT = MODE == kModeStrict;
+    static_assert(!(STRICT && DEEP), "depths beyond shared memory use the reference walk");
     static_assert(U % 2 == 0, "coordinates are processed in f32x2 pairs");
     constexpr int RP = kThreads / VBQ_GROUP;              // rows covered by one pass of the CTA
     constexpr int P = U / 2;                              // coordinate pairs per thread
@@ -67,9 +104,11 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_quantize_kernel(const QArgs a
     __shared__ double sRed[VBQ_TOTALS][kMaxThreads / 32];
     __shared__ bool sLast;
 
-    const int N = a.N;
+    const int N = NT > 0 ? NT : a.N;
     const int NS = min(N, kSmemDepth);                  // depths walked in shared memory
     const int lam = blockIdx.y;
+    const unsigned outm = (a.zhat ? 1u : 0u) | (a.qidx ? 2u : 0u) | (a.level ? 4u : 0u) | (a.bits ? 8u : 0u) |
+                          (a.em_bits ? 16u : 0u) | (a.em ? 32u : 0u) | (a.len ? 64u : 0u);
     const int col = threadIdx.x & (VBQ_GROUP - 1);
     const int rsub = threadIdx.x >> 4;
     const bool logvar = (a.flags & VBQ_FLAG_LOGVAR) != 0;
@@ -84,7 +123,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_quantize_kernel(const QArgs a
     const float *sLenc = sLen + col;
 
     double acc_len = 0.0, acc_em = 0.0, acc_dist = 0.0;
-    long long acc_level = 0;
+    int acc_level = 0;   // < 2^31: at most 2^31/C rows per launch, depth <= 20
 
     long long unit = u0;
     while (unit < u1) {
@@ -203,13 +242,17 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_quantize_kernel(const QArgs a
                 nR[u] = 0;
                 V[u] = mu[u] > z0 ? 96 : 32;
             }
+            bool tie[U];   // kModeStrict: two depths reached exactly the same score
+#pragma unroll
+            for (int u = 0; u < U; ++u) tie[u] = false;
             int m_done = 0;   // deepest level processed (warp-uniform)
 
             // ---- depths 1..10 in shared memory, fully unrolled ------------------------------------------
 #pragma unroll
             for (int n = 1; n <= kSmemDepth; ++n) {
-                if (n > NS) break;
-                if (PRUNE && (n & 1)) {   // sound early exit: every deeper score is <= -penalty < best
+                if (NT == 0 && n > NS) break;
+                if (NT > 0 && n > NT) break;
+                if (PRUNE && n % 3 == 0) {   // sound early exit: every deeper score is <= -penalty < best
                     bool done = true;
 #pragma unroll
                     for (int u = 0; u < U; ++u) done = done && (fmaxf(bestL[u], bestR[u]) > thr[n - 1]);
@@ -231,6 +274,19 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_quantize_kernel(const QArgs a
                     if (FAST) {
                         const float2 s = score_fast2(make_float2(zp[u], zp[v]), make_float2(zn[u], zn[v]), nmu2[k],
                                                      rs2[k], npen2[n]);
+                        if (s.x > bestL[u]) { bestL[u] = s.x; nL[u] = n; }
+                        if (s.y > bestL[v]) { bestL[v] = s.y; nL[v] = n; }
+                    } else if (STRICT) {
+                        // |fl(z-mu)| of the nearer end, then the reference's roundings on it (sign-symmetric)
+                        const float2 dp = __fadd2_rn(make_float2(zp[u], zp[v]), nmu2[k]);
+                        const float2 dn = __fadd2_rn(make_float2(zn[u], zn[v]), nmu2[k]);
+                        const float2 d = make_float2(fminf(fabsf(dp.x), fabsf(dn.x)), fminf(fabsf(dp.y), fabsf(dn.y)));
+                        const float2 q0 = __fmul2_rn(d, rs2[k]);
+                        const float2 e = __ffma2_rn(q0, nsg2[k], d);
+                        const float2 q = __ffma2_rn(e, rs2[k], q0);
+                        const float2 s = __ffma2_rn(__fmul2_rn(q, q), make_float2(-0.5f, -0.5f), npen2[n]);
+                        tie[u] = tie[u] || (s.x == bestL[u]);
+                        tie[v] = tie[v] || (s.y == bestL[v]);
                         if (s.x > bestL[u]) { bestL[u] = s.x; nL[u] = n; }
                         if (s.y > bestL[v]) { bestL[v] = s.y; nL[v] = n; }
                     } else {
@@ -295,8 +351,13 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_quantize_kernel(const QArgs a
             // index at depth m_done + 1), branch-free.
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const bool use_r = !FAST && (bestR[u] > bestL[u]);
-                const int n = use_r ? nR[u] : nL[u];
+                bool use_r = MODE == kModeReference && (bestR[u] > bestL[u]);
+                int n = use_r ? nR[u] : nL[u];
+                if (STRICT && tie[u]) {   // rare: the candidate order matters; redo this coordinate faithfully
+                    const int r = reference_walk(pb, sPen + col, z0, mu[u], sg[u], NS);
+                    n = r & 0xff;
+                    use_r = (r & 0x100) != 0;
+                }
                 const int sh = m_done + 1 - n;
                 const int ipn = idx[u] >> sh;                       // path node at depth n
                 const int d = ((idx[u] >> (sh - 1)) & 1) ? 1 : -1;  // side of the other bracket end
@@ -317,6 +378,13 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_quantize_kernel(const QArgs a
                     const float dp = fabsf(zp - mu[u]), dn = fabsf(zn - mu[u]);
                     path_wins = dp < dn || (dp == dn && zp <= zn);
                 } else {
+                    if (STRICT && !tie[u]) {
+                        // the winning depth is unique: decide left vs right there with the reference's scores
+                        const float rs1 = u & 1 ? rs2[u / 2].y : rs2[u / 2].x;
+                        const float npn = sPen[n * VBQ_GROUP + col];
+                        use_r = score_exact(fmaxf(zp, zn), mu[u], sg[u], rs1, npn) >
+                                score_exact(fminf(zp, zn), mu[u], sg[u], rs1, npn);
+                    }
                     path_wins = use_r ? zp >= zn : zp <= zn;
                 }
                 const int i = path_wins ? ipn : inb;
@@ -324,21 +392,21 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_quantize_kernel(const QArgs a
                 const int q = ((2 * i + 1) << (N - n)) - 1;
                 if (row + u * RP < row_end) {
                     const unsigned o = off + u * off_step;
-                    const float ln = sLenc[n * VBQ_GROUP];
+                    const float ln = (outm & 64u) ? sLenc[n * VBQ_GROUP] : (float)n;
                     float eb = 0.0f;
-                    if (gEm) eb = __ldg(gEm + q);
-                    if (zhat_c) zhat_c[o] = zh;
-                    if (qidx_c) qidx_c[o] = q;
-                    if (level_c) level_c[o] = n;
-                    if (bits_c) bits_c[o] = ln;
-                    if (emb_c) emb_c[o] = eb;
+                    if (outm & 32u) eb = __ldg(gEm + q);
+                    if (outm & 1u) zhat_c[o] = zh;
+                    if (outm & 2u) qidx_c[o] = q;
+                    if (outm & 4u) level_c[o] = n;
+                    if (outm & 8u) bits_c[o] = ln;
+                    if (outm & 16u) emb_c[o] = eb;
                     if (TOTALS) {
-                        const float r1 = FAST ? __frcp_rn(sg[u]) : (u & 1 ? rs2[u / 2].y : rs2[u / 2].x);
-                        const double t = (double)div_rn(__fsub_rn(zh, mu[u]), sg[u], r1);
+                        // distortion of the winner 0.5*t^2 = pen - (-score), up to one float32 rounding of the score
+                        const float best = (MODE == kModeReference && use_r) ? bestR[u] : bestL[u];
                         acc_level += n;
-                        acc_len += (double)ln;
-                        acc_em += (double)eb;
-                        acc_dist += 0.5 * t * t;
+                        if (outm & 64u) acc_len += (double)ln;
+                        if (outm & 32u) acc_em += (double)eb;
+                        acc_dist += (double)sPen[n * VBQ_GROUP + col] - (double)best;
                     }
                 }
             }
@@ -347,7 +415,8 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_quantize_kernel(const QArgs a
     }
 
     if (TOTALS) {
-        double v[VBQ_TOTALS] = {(double)acc_level, acc_len, acc_em, acc_dist};
+        // raw-length mode: the code length of depth n is n itself
+        double v[VBQ_TOTALS] = {(double)acc_level, (outm & 64u) ? acc_len : (double)acc_level, acc_em, acc_dist};
 #pragma unroll
         for (int k = 0; k < VBQ_TOTALS; ++k) {
 #pragma unroll
@@ -415,7 +484,7 @@ extern "C" long long vbq_quantize_workspace_bytes(int n_lambda) {
     return (long long)ticket_bytes(n_lambda) + (long long)n_lambda * kMaxGrid * VBQ_TOTALS * (long long)sizeof(double);
 }
 
-template <bool FAST, bool PRUNE, bool TOTALS, bool DEEP, int U, int T>
+template <int MODE, bool PRUNE, bool TOTALS, bool DEEP, int NT, int U, int T>
 static int launch_quantize(QArgs a, int sms, cudaStream_t st) {
     constexpr int rows_per_pass = T / VBQ_GROUP;
     a.passes = (a.rows + rows_per_pass - 1) / rows_per_pass;
@@ -426,27 +495,36 @@ static int launch_quantize(QArgs a, int sms, cudaStream_t st) {
     if (gx > kMaxGrid) gx = kMaxGrid;
     const size_t smem = ((size_t)kPadEntries * VBQ_GROUP + 3 * (size_t)(a.N + 1) * VBQ_GROUP +
                          (size_t)kStages * 2 * U * T) * sizeof(float);
-    auto kern = vbq_quantize_kernel<FAST, PRUNE, TOTALS, DEEP, U, T>;
+    auto kern = vbq_quantize_kernel<MODE, PRUNE, TOTALS, DEEP, NT, U, T>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3((int)gx, a.n_lambda), T, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return VBQ_OK;
 }
 
-template <bool FAST, bool PRUNE, int U, int T>
+template <int MODE, bool PRUNE, int U, int T>
 static int launch_mode2(const QArgs &a, int sms, cudaStream_t st) {
-    const bool tot = a.totals != nullptr, deep = a.N > kSmemDepth;
-    if (deep) return tot ? launch_quantize<FAST, PRUNE, true, true, U, T>(a, sms, st)
-                         : launch_quantize<FAST, PRUNE, false, true, U, T>(a, sms, st);
-    return tot ? launch_quantize<FAST, PRUNE, true, false, U, T>(a, sms, st)
-               : launch_quantize<FAST, PRUNE, false, false, U, T>(a, sms, st);
+    const bool tot = a.totals != nullptr;
+    if (a.N > kSmemDepth) {   // deep tables: depths 11..N come from global memory, reference walk (or fast)
+        constexpr int M = MODE == kModeStrict ? kModeReference : MODE;
+        return tot ? launch_quantize<M, PRUNE, true, true, 0, U, T>(a, sms, st)
+                   : launch_quantize<M, PRUNE, false, true, 0, U, T>(a, sms, st);
+    }
+    if (a.N == kSmemDepth) return tot ? launch_quantize<MODE, PRUNE, true, false, kSmemDepth, U, T>(a, sms, st)
+                                      : launch_quantize<MODE, PRUNE, false, false, kSmemDepth, U, T>(a, sms, st);
+    return tot ? launch_quantize<MODE, PRUNE, true, false, 0, U, T>(a, sms, st)
+               : launch_quantize<MODE, PRUNE, false, false, 0, U, T>(a, sms, st);
 }
 
 template <int U, int T>
 static int launch_mode(const QArgs &a, int sms, cudaStream_t st) {
-    const bool fast = (a.flags & VBQ_FLAG_FAST) != 0, prune = !(a.flags & VBQ_FLAG_NO_PRUNE);
-    if (fast) return prune ? launch_mode2<true, true, U, T>(a, sms, st) : launch_mode2<true, false, U, T>(a, sms, st);
-    return prune ? launch_mode2<false, true, U, T>(a, sms, st) : launch_mode2<false, false, U, T>(a, sms, st);
+    const bool prune = !(a.flags & VBQ_FLAG_NO_PRUNE);
+    if (a.flags & VBQ_FLAG_FAST)
+        return prune ? launch_mode2<kModeFast, true, U, T>(a, sms, st) : launch_mode2<kModeFast, false, U, T>(a, sms, st);
+    if (a.flags & VBQ_FLAG_REFERENCE_WALK)
+        return prune ? launch_mode2<kModeReference, true, U, T>(a, sms, st)
+                     : launch_mode2<kModeReference, false, U, T>(a, sms, st);
+    return prune ? launch_mode2<kModeStrict, true, U, T>(a, sms, st) : launch_mode2<kModeStrict, false, U, T>(a, sms, st);
 }
 
 extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long rows, int C, const float *d_table,
@@ -458,7 +536,8 @@ extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long r
         return vbq_fail(VBQ_ERR_BAD_SHAPE, "vbq_quantize: rows=%lld C=%d n_lambda=%d pen_channels=%d", rows, C,
                         n_lambda, pen_channels);
     RETURN_IF(vbq_check_depth(N));
-    if (flags & ~(VBQ_FLAG_LOGVAR | VBQ_FLAG_NO_PRUNE | VBQ_FLAG_FAST | VBQ_FLAG_ACCUMULATE_TOTALS | VBQ_FLAG_NO_SWEEP))
+    if (flags & ~(VBQ_FLAG_LOGVAR | VBQ_FLAG_NO_PRUNE | VBQ_FLAG_FAST | VBQ_FLAG_ACCUMULATE_TOTALS | VBQ_FLAG_NO_SWEEP |
+                  VBQ_FLAG_REFERENCE_WALK))
         return vbq_fail(VBQ_ERR_BAD_FLAGS, "vbq_quantize: unknown flag bits 0x%x", flags);
     if (!d_table || !d_packed || !d_penalty || (rows > 0 && (!d_mu || !d_sigma)))
         return vbq_fail(VBQ_ERR_NULL_POINTER, "vbq_quantize: null input pointer");

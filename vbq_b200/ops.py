@@ -22,6 +22,7 @@ FLAG_LOGVAR = _lib.FLAG_LOGVAR
 FLAG_NO_PRUNE = _lib.FLAG_NO_PRUNE
 FLAG_FAST = _lib.FLAG_FAST
 FLAG_NO_SWEEP = _lib.FLAG_NO_SWEEP
+FLAG_REFERENCE_WALK = _lib.FLAG_REFERENCE_WALK
 
 
 def _ptr(t: Optional[torch.Tensor]):
