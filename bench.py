@@ -240,6 +240,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     prior, q = make_prior_and_quantizer(dev)
     pen, length = q._length_tables([LAMB])
+    args.flags = ops.search_flags([LAMB], args.flags)   # what the facade passes for this lambda
 
     # rotating buffer sets so that no step finds its inputs in the 126 MB L2
     set_bytes = COORDS * BYTES_PER_COORD

@@ -136,8 +136,14 @@ extern "C" int vbq_quantize_host(vbq_host_ctx *c, const float *h_mu, const float
         CUDA_TRY(cudaStreamWaitEvent(c->s_out, s.done, 0));
         const size_t w = nr * row_bytes, hp = (size_t)rows * row_bytes;
 #define D2H(hp_, dp_)                                                                                         \
-    if (hp_) CUDA_TRY(cudaMemcpy2DAsync((char *)(hp_) + (size_t)r0 * row_bytes, hp, dp_, w, w, (size_t)L,       \
-                                        cudaMemcpyDeviceToHost, c->s_out))
+    if (hp_) {                                                                                                \
+        if (L == 1)                                                                                           \
+            CUDA_TRY(cudaMemcpyAsync((char *)(hp_) + (size_t)r0 * row_bytes, dp_, w, cudaMemcpyDeviceToHost,  \
+                                     c->s_out));                                                              \
+        else                                                                                                  \
+            CUDA_TRY(cudaMemcpy2DAsync((char *)(hp_) + (size_t)r0 * row_bytes, hp, dp_, w, w, (size_t)L,      \
+                                       cudaMemcpyDeviceToHost, c->s_out));                                    \
+    }
         D2H(h_zhat, s.zhat);
         D2H(h_qidx, s.qidx);
         D2H(h_level, s.level);

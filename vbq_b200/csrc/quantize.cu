@@ -107,8 +107,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_quantize_kernel(const QArgs a
     const int N = NT > 0 ? NT : a.N;
     const int NS = min(N, kSmemDepth);                  // depths walked in shared memory
     const int lam = blockIdx.y;
-    const unsigned outm = (a.zhat ? 1u : 0u) | (a.qidx ? 2u : 0u) | (a.level ? 4u : 0u) | (a.bits ? 8u : 0u) |
-                          (a.em_bits ? 16u : 0u) | (a.em ? 32u : 0u) | (a.len ? 64u : 0u);
+    const unsigned outm = a.outm;   // bit k set: zhat, qidx, level, bits, em_bits requested; 32: entropy model; 64: lengths
     const int col = threadIdx.x & (VBQ_GROUP - 1);
     const int rsub = threadIdx.x >> 4;
     const bool logvar = (a.flags & VBQ_FLAG_LOGVAR) != 0;
@@ -556,6 +555,8 @@ extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long r
     a.zhat = d_zhat; a.qidx = d_qidx; a.level = d_level; a.bits = d_bits; a.em_bits = d_em_bits;
     a.totals = d_totals; a.partials = nullptr; a.ticket = nullptr;
     a.flags = flags;
+    a.outm = (d_zhat ? 1u : 0u) | (d_qidx ? 2u : 0u) | (d_level ? 4u : 0u) | (d_bits ? 8u : 0u) |
+             (d_em_bits ? 16u : 0u) | (d_entropy_model ? 32u : 0u) | (d_length ? 64u : 0u);
     a.n_groups = (C + VBQ_GROUP - 1) / VBQ_GROUP;
 
     if (d_totals) {

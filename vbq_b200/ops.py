@@ -44,6 +44,16 @@ def _need_cuda(name, t, dtype, ndim=None):
         raise ValueError("vbq_b200: `%s` must be %d-D, got shape %s" % (name, ndim, tuple(t.shape)))
 
 
+def search_flags(lambs, flags=0):
+    """Flags the facade passes to vbq_quantize for a list of rate-distortion trade-offs.  The sound early exit
+    ("every deeper score is <= -penalty") only pays off when the penalty grows quickly with depth; for small lambdas
+    the walk reaches the bottom anyway and the exit tests are pure overhead, so they are compiled out.  Results are
+    identical either way (tests/test_gpu_parity.py::test_prune_equals_no_prune_large)."""
+    if len(lambs) == 1 and float(lambs[0]) < 1.0:
+        flags |= FLAG_NO_PRUNE
+    return flags
+
+
 def num_levels(max_bits: int) -> int:
     return 2 ** (max_bits + 1) - 1
 

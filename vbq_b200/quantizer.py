@@ -122,6 +122,7 @@ class ChannelwisePriorCDFQuantizer:
             outputs |= ops.OUT_EM_BITS
         if logvar:
             flags |= ops.FLAG_LOGVAR
+        flags = ops.search_flags(lambs, flags)
         z, q, lv, b, eb, tot = ops.quantize(means, scales, self.all_code_points, self._packed, pen, length, em,
                                             self.max_bits_per_coord, outputs, flags)
         return dict(zhat=z, qidx=q, level=lv, bits=b, em_bits=eb, totals=tot)

@@ -62,7 +62,8 @@ class GaussianCodebook:
             m = torch.cat([m, m.new_zeros(pad)])
             s = torch.cat([s, s.new_ones(pad)])
         z, q, lv, b, _, tot = ops.quantize(m.reshape(-1, _VC).contiguous(), s.reshape(-1, _VC).contiguous(),
-                                           self._table, self._packed, pen, length, None, N, outputs, flags)
+                                           self._table, self._packed, pen, length, None, N, outputs,
+                                           ops.search_flags(betas, flags))
         L = len(betas)
 
         def unpad(t):
