@@ -346,7 +346,7 @@ def run_ours(args, rank, world, local_rank):
     peaks, peak_kind = measured_peaks()
     traffic = None
     tp = os.path.join(ROOT, "profiles", "r1_traffic.json")   # dram__bytes_read+write of one ncu --set full capture
-    if os.path.exists(tp) and args.flags == 0:
+    if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f)["traffic_bytes_per_launch"]
     kern_ms = float(np.median(per_launch_ms))
