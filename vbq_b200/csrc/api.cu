@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "common.h"
 
 static thread_local char g_err[512] = "";
@@ -14,10 +16,23 @@ int vbq_fail(int code, const char *fmt, ...) {
     return code;
 }
 
+// Device ordinal and SM count of the current device.  The SM count never changes, so it is cached per ordinal
+// (a benign, idempotent cache: the only process-wide state of the library besides the thread-local error text).
+int vbq_current_device(int *dev, int *sms) {
+    static std::atomic<int> cache[64];
+    CUDA_TRY(cudaGetDevice(dev));
+    int n = (*dev >= 0 && *dev < 64) ? cache[*dev].load(std::memory_order_relaxed) : 0;
+    if (n == 0) {
+        CUDA_TRY(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, *dev));
+        if (*dev >= 0 && *dev < 64) cache[*dev].store(n, std::memory_order_relaxed);
+    }
+    *sms = n;
+    return VBQ_OK;
+}
+
 int vbq_grid_for(long long total, int block, int *grid) {
     int dev = 0, sms = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    RETURN_IF(vbq_current_device(&dev, &sms));
     long long need = (total + block - 1) / block;
     long long cap = (long long)sms * 16;
     *grid = (int)(need < 1 ? 1 : (need > cap ? cap : need));

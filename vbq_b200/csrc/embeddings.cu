@@ -76,7 +76,9 @@ extern "C" int vbq_compress_coordinates_f64(const float *d_mu, const float *d_si
     int grid;
     RETURN_IF(vbq_grid_for(n, kEmbThreads, &grid));
     const size_t smem = ((size_t)((1 << (N + 1)) - 1) + N + 1) * sizeof(double);
-    CUDA_TRY(cudaFuncSetAttribute(embeddings_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 0;
+    RETURN_IF(vbq_current_device(&dev, &sms));
+    VBQ_ENSURE_MAX_SMEM(embeddings_f64_kernel, dev);
     embeddings_f64_kernel<<<grid, kEmbThreads, smem, (cudaStream_t)stream>>>(
         d_mu, d_sigma, n, d_codepoints, N, d_lengths, 2.0 * beta, pen_f32, d_optima, d_heap_index, d_level);
     CUDA_TRY(cudaGetLastError());

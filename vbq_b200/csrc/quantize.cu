@@ -484,7 +484,7 @@ extern "C" long long vbq_quantize_workspace_bytes(int n_lambda) {
 }
 
 template <int MODE, bool PRUNE, bool TOTALS, bool DEEP, int NT, int U, int T>
-static int launch_quantize(QArgs a, int sms, cudaStream_t st) {
+static int launch_quantize(QArgs a, int dev, int sms, cudaStream_t st) {
     constexpr int rows_per_pass = T / VBQ_GROUP;
     a.passes = (a.rows + rows_per_pass - 1) / rows_per_pass;
     a.total_units = a.passes * a.n_groups;
@@ -495,35 +495,35 @@ static int launch_quantize(QArgs a, int sms, cudaStream_t st) {
     const size_t smem = ((size_t)kPadEntries * VBQ_GROUP + 3 * (size_t)(a.N + 1) * VBQ_GROUP +
                          (size_t)kStages * 2 * U * T) * sizeof(float);
     auto kern = vbq_quantize_kernel<MODE, PRUNE, TOTALS, DEEP, NT, U, T>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VBQ_ENSURE_MAX_SMEM(kern, dev);
     kern<<<dim3((int)gx, a.n_lambda), T, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return VBQ_OK;
 }
 
 template <int MODE, bool PRUNE, int U, int T>
-static int launch_mode2(const QArgs &a, int sms, cudaStream_t st) {
+static int launch_mode2(const QArgs &a, int dev, int sms, cudaStream_t st) {
     const bool tot = a.totals != nullptr;
     if (a.N > kSmemDepth) {   // deep tables: depths 11..N come from global memory, reference walk (or fast)
         constexpr int M = MODE == kModeStrict ? kModeReference : MODE;
-        return tot ? launch_quantize<M, PRUNE, true, true, 0, U, T>(a, sms, st)
-                   : launch_quantize<M, PRUNE, false, true, 0, U, T>(a, sms, st);
+        return tot ? launch_quantize<M, PRUNE, true, true, 0, U, T>(a, dev, sms, st)
+                   : launch_quantize<M, PRUNE, false, true, 0, U, T>(a, dev, sms, st);
     }
-    if (a.N == kSmemDepth) return tot ? launch_quantize<MODE, PRUNE, true, false, kSmemDepth, U, T>(a, sms, st)
-                                      : launch_quantize<MODE, PRUNE, false, false, kSmemDepth, U, T>(a, sms, st);
-    return tot ? launch_quantize<MODE, PRUNE, true, false, 0, U, T>(a, sms, st)
-               : launch_quantize<MODE, PRUNE, false, false, 0, U, T>(a, sms, st);
+    if (a.N == kSmemDepth) return tot ? launch_quantize<MODE, PRUNE, true, false, kSmemDepth, U, T>(a, dev, sms, st)
+                                      : launch_quantize<MODE, PRUNE, false, false, kSmemDepth, U, T>(a, dev, sms, st);
+    return tot ? launch_quantize<MODE, PRUNE, true, false, 0, U, T>(a, dev, sms, st)
+               : launch_quantize<MODE, PRUNE, false, false, 0, U, T>(a, dev, sms, st);
 }
 
 template <int U, int T>
-static int launch_mode(const QArgs &a, int sms, cudaStream_t st) {
+static int launch_mode(const QArgs &a, int dev, int sms, cudaStream_t st) {
     const bool prune = !(a.flags & VBQ_FLAG_NO_PRUNE);
     if (a.flags & VBQ_FLAG_FAST)
-        return prune ? launch_mode2<kModeFast, true, U, T>(a, sms, st) : launch_mode2<kModeFast, false, U, T>(a, sms, st);
+        return prune ? launch_mode2<kModeFast, true, U, T>(a, dev, sms, st) : launch_mode2<kModeFast, false, U, T>(a, dev, sms, st);
     if (a.flags & VBQ_FLAG_REFERENCE_WALK)
-        return prune ? launch_mode2<kModeReference, true, U, T>(a, sms, st)
-                     : launch_mode2<kModeReference, false, U, T>(a, sms, st);
-    return prune ? launch_mode2<kModeStrict, true, U, T>(a, sms, st) : launch_mode2<kModeStrict, false, U, T>(a, sms, st);
+        return prune ? launch_mode2<kModeReference, true, U, T>(a, dev, sms, st)
+                     : launch_mode2<kModeReference, false, U, T>(a, dev, sms, st);
+    return prune ? launch_mode2<kModeStrict, true, U, T>(a, dev, sms, st) : launch_mode2<kModeStrict, false, U, T>(a, dev, sms, st);
 }
 
 extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long rows, int C, const float *d_table,
@@ -576,11 +576,9 @@ extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long r
     }
 
     int dev = 0, sms = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    // tuning override (development only): VBQ_TUNE=<U><threads/256>, e.g. 22 = U 2, 512 threads
-    int tune = 22;
-    if (const char *e = getenv("VBQ_TUNE")) tune = atoi(e);
+    RETURN_IF(vbq_current_device(&dev, &sms));
+    // tuning override (development only, read once): VBQ_TUNE=<U><threads/256>, e.g. 22 = U 2, 512 threads
+    static const int tune = getenv("VBQ_TUNE") ? atoi(getenv("VBQ_TUNE")) : 22;
     // the kernel indexes a channel-last array with 32-bit element offsets: split very large calls into row chunks
     const long long max_chunk_rows = ((1ll << 31) - 1) / C > 1 ? (((1ll << 31) - 1) / C) & ~1023ll : 1;
     a.lam_stride = rows * (long long)C;
@@ -599,17 +597,17 @@ extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long r
         b.accumulate = r0 > 0 || (flags & VBQ_FLAG_ACCUMULATE_TOTALS);
         int st_;
         if (!(flags & VBQ_FLAG_NO_SWEEP)) {   // several lambdas: one walk per coordinate serves all of them
-            st_ = vbq_launch_sweep(b, sms, st);
+            st_ = vbq_launch_sweep(b, dev, sms, st);
             if (st_ >= 0) {
                 RETURN_IF(st_);
                 continue;
             }
         }
         switch (tune) {
-            case 23: st_ = launch_mode<2, 768>(b, sms, st); break;
-            case 42: st_ = launch_mode<4, 512>(b, sms, st); break;
-            case 41: st_ = launch_mode<4, 256>(b, sms, st); break;
-            default: st_ = launch_mode<2, 512>(b, sms, st); break;
+            case 23: st_ = launch_mode<2, 768>(b, dev, sms, st); break;
+            case 42: st_ = launch_mode<4, 512>(b, dev, sms, st); break;
+            case 41: st_ = launch_mode<4, 256>(b, dev, sms, st); break;
+            default: st_ = launch_mode<2, 512>(b, dev, sms, st); break;
         }
         RETURN_IF(st_);
     }

@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_sweep_kernel(const QArgs a) {
 }
 
 template <bool FAST, bool TOTALS, int T, int LP>
-static int launch_sweep_t(QArgs a, int sms, cudaStream_t st) {
+static int launch_sweep_t(QArgs a, int dev, int sms, cudaStream_t st) {
     constexpr int U = 2;
     constexpr int rows_per_pass = T / VBQ_GROUP;
     a.passes = (a.rows + rows_per_pass - 1) / rows_per_pass;
@@ -332,7 +332,7 @@ static int launch_sweep_t(QArgs a, int sms, cudaStream_t st) {
             b.partials = a.partials + (size_t)l0 * kMaxGrid * VBQ_TOTALS;
         }
         const size_t smem = fixed + per_lambda * b.n_lambda;
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        VBQ_ENSURE_MAX_SMEM(kern, dev);
         kern<<<dim3((int)gx, 1), T, smem, st>>>(b);
         CUDA_TRY(cudaGetLastError());
     }
@@ -340,14 +340,14 @@ static int launch_sweep_t(QArgs a, int sms, cudaStream_t st) {
 }
 
 // returns -1 when the sweep does not apply (caller uses the per-lambda kernel), else a VBQ_* status
-int vbq_launch_sweep(const QArgs &a, int sms, cudaStream_t st) {
+int vbq_launch_sweep(const QArgs &a, int dev, int sms, cudaStream_t st) {
     if (a.N > kSmemDepth || a.n_lambda < 2) return -1;
     const bool fast = (a.flags & VBQ_FLAG_FAST) != 0, tot = a.totals != nullptr;
-    int tune = 41;   // development override: VBQ_SWEEP_TUNE=<threads/128><lambdas per group>
-    if (const char *e = getenv("VBQ_SWEEP_TUNE")) tune = atoi(e);
+    // development override (read once): VBQ_SWEEP_TUNE=<threads/128><lambdas per group>
+    static const int tune = getenv("VBQ_SWEEP_TUNE") ? atoi(getenv("VBQ_SWEEP_TUNE")) : 41;
 #define SWEEP_CASE(T, LP)                                                                                        \
-    if (fast) return tot ? launch_sweep_t<true, true, T, LP>(a, sms, st) : launch_sweep_t<true, false, T, LP>(a, sms, st); \
-    return tot ? launch_sweep_t<false, true, T, LP>(a, sms, st) : launch_sweep_t<false, false, T, LP>(a, sms, st);
+    if (fast) return tot ? launch_sweep_t<true, true, T, LP>(a, dev, sms, st) : launch_sweep_t<true, false, T, LP>(a, dev, sms, st); \
+    return tot ? launch_sweep_t<false, true, T, LP>(a, dev, sms, st) : launch_sweep_t<false, false, T, LP>(a, dev, sms, st);
     switch (tune) {
         case 21: { SWEEP_CASE(256, 1) }
         case 24: { SWEEP_CASE(256, 4) }
