@@ -605,6 +605,7 @@ extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long r
         }
         switch (tune) {
             case 23: st_ = launch_mode<2, 768>(b, dev, sms, st); break;
+            case 25: st_ = launch_mode<2, 640>(b, dev, sms, st); break;
             case 42: st_ = launch_mode<4, 512>(b, dev, sms, st); break;
             case 41: st_ = launch_mode<4, 256>(b, dev, sms, st); break;
             default: st_ = launch_mode<2, 512>(b, dev, sms, st); break;
