@@ -389,7 +389,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--flags", type=int, default=0, help="VBQ_FLAG_* bits passed to vbq_quantize")
-    ap.add_argument("--chunk-rows", type=int, default=4608, help="rows per chunk of the host pipeline (e2e leg)")
+    ap.add_argument("--chunk-rows", type=int, default=9216, help="rows per chunk of the host pipeline (e2e leg)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
