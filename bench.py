@@ -354,11 +354,11 @@ def run_ours(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu:
         b = sets[0]
-        n_img = 8
+        n_img = IMAGES
         v, dt = cpu_throughput(q.all_code_points.cpu().numpy(), b["mu"][:n_img * H * W].cpu().numpy(),
                                b["sigma"][:n_img * H * W].cpu().numpy(), n_img, 1)
         cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "%d of the 24 Kodak-shaped images (%d coordinates), one image per call, %.1f s"
+               "sample": "%d of the 24 Kodak-shaped images (%d coordinates), one image per call, single process, %.1f s"
                          % (n_img, n_img * H * W * C, dt)}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -261,3 +261,30 @@ def test_massive_ties_follow_argmax_order(flags):
     for i, l in enumerate(lambs):
         assert np.array_equal(out["zhat"][i].cpu().numpy(), Zo[l]), l
         assert np.array_equal(out["level"][i].cpu().numpy(), Bo[l]), l
+
+
+@pytest.mark.parametrize("flags", [0, 4, 32])
+def test_garbage_inputs_stay_in_bounds(flags):
+    """The reference does not validate inputs (NaNs propagate silently); the kernel must at least terminate
+    and keep every index inside its table for NaN / inf / zero / negative posteriors."""
+    import vbq_b200
+    from vbq_b200 import ops
+    C, N, rows = 16, 10, 512
+    pr = H.make_prior(C, seed=1)
+    q = vbq_b200.ChannelwisePriorCDFQuantizer(C, N)
+    q.set_code_points(ops.build_code_points_learned(_dev(pr.packed()), N))
+    mu, sigma, _ = H.make_latents(pr, rows, 2)
+    bad = [np.nan, np.inf, -np.inf, 0.0, -1.0, 1e-45, 3e38]
+    for k, v in enumerate(bad):
+        mu[k::32, k % C] = v if k < 3 else mu[k::32, k % C]
+        sigma[k::32, (k + 5) % C] = v
+    for lambs in ([0.5], [0.0, 0.5, 8.0]):
+        out = q.quantize(_dev(mu), _dev(sigma), lambs, flags=flags,
+                         outputs=ops.OUT_ZHAT | ops.OUT_QIDX | ops.OUT_LEVEL | ops.OUT_TOTALS)
+        torch.cuda.synchronize()
+        qi, lv = out["qidx"].cpu().numpy(), out["level"].cpu().numpy()
+        assert qi.min() >= 0 and qi.max() < q.quantization_levels
+        assert lv.min() >= 0 and lv.max() <= N
+        srt = q.code_points_by_channel.cpu().numpy()
+        for i in range(len(lambs)):
+            assert np.array_equal(np.take_along_axis(srt.T, qi[i].astype(np.int64), axis=0), out["zhat"][i].cpu().numpy())
