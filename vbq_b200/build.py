@@ -7,14 +7,16 @@ import subprocess
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_DIR = os.path.dirname(PKG_DIR)
-SOURCES = [os.path.join(PKG_DIR, "csrc", f) for f in ("api.cu", "priors.cu", "quantize.cu", "sweep.cu", "host_pipeline.cu", "operators.cu", "embeddings.cu")]
+SOURCES = [os.path.join(PKG_DIR, "csrc", f) for f in ("api.cu", "priors.cu", "quantize.cu", "quantize_strict.cu", "quantize_reference.cu", "quantize_fast.cu",
+            "sweep.cu", "host_pipeline.cu", "operators.cu", "embeddings.cu")]
 HEADERS = [os.path.join(REPO_DIR, "include", "vbq_b200.h"), os.path.join(PKG_DIR, "csrc", "common.h"),
-           os.path.join(PKG_DIR, "csrc", "tree.cuh")]
+           os.path.join(PKG_DIR, "csrc", "tree.cuh"),
+           os.path.join(PKG_DIR, "csrc", "quantize_kernel.cuh")]
 LIB_PATH = os.path.join(PKG_DIR, "libvbq_b200.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-O3", "-lineinfo", "-std=c++17",
+    "-O3", "-lineinfo", "-std=c++17", "--threads", "0",
     "-Xcompiler", "-fPIC", "-shared",
 ]
 
