@@ -230,6 +230,20 @@ def run_reference(args, rank, world):
 # --------------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's host threads to the CPUs that are local to its GPU (NVML affinity) before any pinned host
+    buffer is allocated, so that the e2e leg's PCIe traffic does not cross sockets.  Best effort."""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+        nv.nvmlDeviceSetCpuAffinity(nv.nvmlDeviceGetHandleByIndex(phys))
+    except Exception:
+        pass
+
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -238,9 +252,12 @@ def run_ours(args, rank, world, local_rank):
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    bind_to_gpu_numa_node(local_rank)
     prior, q = make_prior_and_quantizer(dev)
     pen, length = q._length_tables([LAMB])
     args.flags = ops.search_flags([LAMB], args.flags)   # what the facade passes for this lambda
+    if world > 1 and not args.no_reserve:
+        args.flags |= ops.FLAG_RESERVE_SM               # leave one SM to the overlapped NCCL all-reduce
 
     # rotating buffer sets so that no step finds its inputs in the 126 MB L2
     set_bytes = COORDS * BYTES_PER_COORD
@@ -390,6 +407,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--flags", type=int, default=0, help="VBQ_FLAG_* bits passed to vbq_quantize")
     ap.add_argument("--chunk-rows", type=int, default=9216, help="rows per chunk of the host pipeline (e2e leg)")
+    ap.add_argument("--no-reserve", action="store_true", help="multi-GPU: do not leave an SM to the NCCL kernel")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -53,6 +53,8 @@ enum {
 /* flags of vbq_quantize */
 #define VBQ_FLAG_LOGVAR   1u     /* d_sigma holds log-variances; sigma = sqrt(exp(logvar)) (quantizer.py:193-198) */
 #define VBQ_FLAG_NO_PRUNE 2u     /* visit every bit depth even when deeper levels provably cannot win */
+#define VBQ_FLAG_RESERVE_SM 64u       /* launch one CTA fewer than there are SMs, so that a concurrent kernel on another
+                                         stream (e.g. the NCCL all-reduce of the previous call's totals) finds a free SM */
 #define VBQ_FLAG_REFERENCE_WALK 32u   /* score both bracket ends of every depth (the slower, literal formulation; same results) */
 #define VBQ_FLAG_NO_SWEEP 16u         /* walk the tree once per lambda instead of once for all lambdas */
 #define VBQ_FLAG_ACCUMULATE_TOTALS 8u /* add this call's sums to d_totals instead of overwriting them */

@@ -16,6 +16,7 @@ FLAG_FAST = 4
 FLAG_ACCUMULATE_TOTALS = 8
 FLAG_NO_SWEEP = 16
 FLAG_REFERENCE_WALK = 32
+FLAG_RESERVE_SM = 64
 GROUP = 16
 TOTALS = 4
 PRIOR_PARAMS = 43

@@ -98,7 +98,7 @@ extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long r
                         n_lambda, pen_channels);
     RETURN_IF(vbq_check_depth(N));
     if (flags & ~(VBQ_FLAG_LOGVAR | VBQ_FLAG_NO_PRUNE | VBQ_FLAG_FAST | VBQ_FLAG_ACCUMULATE_TOTALS | VBQ_FLAG_NO_SWEEP |
-                  VBQ_FLAG_REFERENCE_WALK))
+                  VBQ_FLAG_REFERENCE_WALK | VBQ_FLAG_RESERVE_SM))
         return vbq_fail(VBQ_ERR_BAD_FLAGS, "vbq_quantize: unknown flag bits 0x%x", flags);
     if (!d_table || !d_packed || !d_penalty || (rows > 0 && (!d_mu || !d_sigma)))
         return vbq_fail(VBQ_ERR_NULL_POINTER, "vbq_quantize: null input pointer");
@@ -139,6 +139,7 @@ extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long r
 
     int dev = 0, sms = 0;
     RETURN_IF(vbq_current_device(&dev, &sms));
+    if ((flags & VBQ_FLAG_RESERVE_SM) && sms > 1) --sms;
     // the kernel addresses a channel-last array with 32-bit BYTE offsets: split calls beyond 2^29 elements into row chunks
     const long long max_chunk_rows = ((1ll << 29) - 1) / C > 1024 ? (((1ll << 29) - 1) / C) & ~1023ll : ((1ll << 29) - 1) / C;
     a.lam_stride = rows * (long long)C;

@@ -23,6 +23,7 @@ FLAG_NO_PRUNE = _lib.FLAG_NO_PRUNE
 FLAG_FAST = _lib.FLAG_FAST
 FLAG_NO_SWEEP = _lib.FLAG_NO_SWEEP
 FLAG_REFERENCE_WALK = _lib.FLAG_REFERENCE_WALK
+FLAG_RESERVE_SM = _lib.FLAG_RESERVE_SM
 
 
 def _ptr(t: Optional[torch.Tensor]):
