@@ -1,13 +1,17 @@
 #!/bin/bash
 # development helper: sweep-kernel tuning (VBQ_SWEEP_TUNE=<threads/128><lambdas per group>)
-python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "sweep or index_parity" 2>&1 | tail -2
-for t in 22 21 24 41 42 32; do
+python -m pytest tests -m gpu -q -x 2>&1 | tail -3
+for t in ${TUNES:-41 51 61}; do
 VBQ_SWEEP_TUNE=$t python - <<PY
 import json, sys
 sys.path.insert(0, "scripts"); sys.path.insert(0, ".")
 import bench_configs as b
+from vbq_b200 import ops
 for L in (16, 64):
-    r = b.sweep_case(L, 0, outputs=False)
-    print("tune $t L", L, "%.1f G coord*lambda/s" % (r["coord_lambda_per_s"] / 1e9))
+    for f in (0, ops.FLAG_REFERENCE_WALK, ops.FLAG_FAST):
+        r = b.sweep_case(L, f, outputs=False)
+        print("tune $t L", L, "flags", f, "%.1f G coord*lambda/s" % (r["coord_lambda_per_s"] / 1e9))
+r = b.sweep_case(16, 0, outputs=True)
+print("tune $t L 16 full outputs %.1f G" % (r["coord_lambda_per_s"] / 1e9))
 PY
 done

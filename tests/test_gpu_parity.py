@@ -255,12 +255,12 @@ def test_massive_ties_follow_argmax_order(flags):
     oq = O.QuantizerNP(C, N)
     oq.set_code_points(table)
     lambs = [0.0, 1e-30, 0.5]
-    out = q.quantize(_dev(mu), _dev(sigma), lambs, flags=flags | ops.FLAG_NO_SWEEP,
-                     outputs=ops.OUT_ZHAT | ops.OUT_LEVEL)
     Zo, Bo = oq.compress_batch_channel_latents(mu, sigma, lambs)
-    for i, l in enumerate(lambs):
-        assert np.array_equal(out["zhat"][i].cpu().numpy(), Zo[l]), l
-        assert np.array_equal(out["level"][i].cpu().numpy(), Bo[l]), l
+    for sweep in (ops.FLAG_NO_SWEEP, 0):
+        out = q.quantize(_dev(mu), _dev(sigma), lambs, flags=flags | sweep, outputs=ops.OUT_ZHAT | ops.OUT_LEVEL)
+        for i, l in enumerate(lambs):
+            assert np.array_equal(out["zhat"][i].cpu().numpy(), Zo[l]), (l, sweep)
+            assert np.array_equal(out["level"][i].cpu().numpy(), Bo[l]), (l, sweep)
 
 
 @pytest.mark.parametrize("flags", [0, 4, 32])

@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_sweep_kernel(const QArgs a) {
                 stage_rows(row + (kStages - 1) * U * RP, off + (kStages - 1) * U * off_step, ps);
                 slot = slot == kStages - 1 ? 0 : slot + 1;
             }
-            const float r0 = __frcp_rn(sg[0]), r1 = __frcp_rn(sg[1]);
+            const float r0 = rcp_rn(sg[0]), r1 = rcp_rn(sg[1]);
             const float2 nmu2 = make_float2(-mu[0], -mu[1]);
             const float2 nsg2 = make_float2(-sg[0], -sg[1]);
             const float2 rs2 = FAST ? make_float2(-0.5f * r0 * r0, -0.5f * r1 * r1) : make_float2(r0, r1);
@@ -344,18 +344,14 @@ int vbq_launch_sweep(const QArgs &a, int dev, int sms, cudaStream_t st) {
     if (a.N > kSmemDepth || a.n_lambda < 2) return -1;
     const bool fast = (a.flags & VBQ_FLAG_FAST) != 0, tot = a.totals != nullptr;
     // development override (read once): VBQ_SWEEP_TUNE=<threads/128><lambdas per group>
-    static const int tune = getenv("VBQ_SWEEP_TUNE") ? atoi(getenv("VBQ_SWEEP_TUNE")) : 41;
+    static const int tune = getenv("VBQ_SWEEP_TUNE") ? atoi(getenv("VBQ_SWEEP_TUNE")) : 61;
 #define SWEEP_CASE(T, LP)                                                                                        \
     if (fast) return tot ? launch_sweep_t<true, true, T, LP>(a, dev, sms, st) : launch_sweep_t<true, false, T, LP>(a, dev, sms, st); \
     return tot ? launch_sweep_t<false, true, T, LP>(a, dev, sms, st) : launch_sweep_t<false, false, T, LP>(a, dev, sms, st);
     switch (tune) {
-        case 21: { SWEEP_CASE(256, 1) }
-        case 24: { SWEEP_CASE(256, 4) }
-        case 42: { SWEEP_CASE(512, 2) }
-        case 32: { SWEEP_CASE(384, 2) }
-        case 22: { SWEEP_CASE(256, 2) }
         case 51: { SWEEP_CASE(640, 1) }
-        default: { SWEEP_CASE(512, 1) }
+        case 41: { SWEEP_CASE(512, 1) }
+        default: { SWEEP_CASE(768, 1) }
     }
 #undef SWEEP_CASE
 }
