@@ -1,5 +1,5 @@
 #!/bin/bash
-# One profiling pass for profiles/: launch list of the bench command, then a full-set capture of the hot kernel.
+# One profiling pass for profiles/: launch list of the bench command, then a full-set capture of the hot kernels.
 set -x
 R=${ROUND:-r1}
 mkdir -p gpurun_out
@@ -9,5 +9,7 @@ ncu --set full --clock-control none --import-source on -k regex:vbq_quantize -s 
     python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/${R}_quantize.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:vbq_sweep -s 2 -c 1 -o gpurun_out/${R}_sweep \
     python scripts/bench_configs.py sweep > gpurun_out/${R}_sweep.log 2>&1
-python bench.py --steps 50 --warmup 5 > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err
-tail -1 gpurun_out/${R}_bench.json
+python bench.py > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err
+python scripts/bench_configs.py > gpurun_out/${R}_configs.jsonl 2> gpurun_out/${R}_configs.err
+python scripts/bench_per_image.py > gpurun_out/${R}_per_image.json 2> gpurun_out/${R}_per_image.err
+tail -1 gpurun_out/${R}_bench.json; cat gpurun_out/${R}_per_image.json; tail -3 gpurun_out/${R}_per_image.err

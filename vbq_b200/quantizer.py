@@ -142,14 +142,13 @@ class ChannelwisePriorCDFQuantizer:
         m, s = self._prep(batch_means, batch_stds)
         corrected = bool(self.raw_code_length_entropy_models)
         out = self.quantize(m, s, lambs, outputs=ops.OUT_ZHAT | (ops.OUT_BITS if corrected else ops.OUT_LEVEL))
+        zs, nbs = out['zhat'], (out['bits'] if corrected else out['level'])
+        if return_np:                      # one device-to-host copy per output, then per-lambda views
+            zs, nbs = utils.to_host_numpy(zs), utils.to_host_numpy(nbs)
         Z_hat_dict, num_bits_dict = {}, {}
         for i, lamb in enumerate(lambs):
-            z = out['zhat'][i]
-            nb = out['bits'][i] if corrected else out['level'][i]
-            if return_np:
-                z, nb = z.cpu().numpy(), nb.cpu().numpy()
-            Z_hat_dict[lamb] = z
-            num_bits_dict[lamb] = nb
+            Z_hat_dict[lamb] = zs[i]
+            num_bits_dict[lamb] = nbs[i]
         return Z_hat_dict, num_bits_dict
 
     def compress_latents(self, posterior_means, posterior_logvars, lambs):
@@ -166,13 +165,17 @@ class ChannelwisePriorCDFQuantizer:
                             outputs=ops.OUT_ZHAT | (ops.OUT_BITS if corrected else ops.OUT_LEVEL))
         out_keys = ('Z_hat', 'raw_num_bits', 'num_bits_cl', 'num_bits')
         output = {key: dict() for key in out_keys}
+        # one device-to-host copy per output tensor (the reference's np.reshape moves to the CPU, quantizer.py:237)
+        zs = utils.to_host_numpy(out['zhat'])
+        raws = utils.to_host_numpy(out['bits'] if corrected else out['level'])
+        ems = utils.to_host_numpy(out['em_bits'])
         for i, lamb in enumerate(lambs):
-            raw = (out['bits'][i] if corrected else out['level'][i]).cpu().numpy().reshape(shape)
-            output['Z_hat'][lamb] = out['zhat'][i].cpu().numpy().reshape(shape)
+            raw = raws[i].reshape(shape)
+            output['Z_hat'][lamb] = zs[i].reshape(shape)
             output['raw_num_bits'][lamb] = raw
             if corrected:
                 output['num_bits_cl'][lamb] = raw
-            output['num_bits'][lamb] = out['em_bits'][i].cpu().numpy().reshape(shape)
+            output['num_bits'][lamb] = ems[i].reshape(shape)
         return output
 
     def compress(self, X, vae, lambs, clip=True):

@@ -47,6 +47,17 @@ def as_device_f32(x, device):
     return torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).to(device)
 
 
+def to_host_numpy(t):
+    """Device tensor -> NumPy array through a pinned staging buffer (PyTorch caches pinned blocks, so repeated calls
+    of the same size pay one DMA at PCIe speed instead of a pageable copy)."""
+    if not t.is_cuda:
+        return t.numpy()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return h.numpy()
+
+
 def lambda_key_list(lambs):
     """The reference keys its dicts by the lambda objects themselves (quantizer.py:172,226)."""
     return list(lambs)
