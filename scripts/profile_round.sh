@@ -11,5 +11,5 @@ ncu --set full --clock-control none --import-source on -k regex:vbq_sweep -s 2 -
     python scripts/bench_configs.py sweep > gpurun_out/${R}_sweep.log 2>&1
 python bench.py > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err
 python scripts/bench_configs.py > gpurun_out/${R}_configs.jsonl 2> gpurun_out/${R}_configs.err
-python scripts/bench_per_image.py > gpurun_out/${R}_per_image.json 2> gpurun_out/${R}_per_image.err
+python tests/bench_per_image.py > gpurun_out/${R}_per_image.json 2> gpurun_out/${R}_per_image.err
 tail -1 gpurun_out/${R}_bench.json; cat gpurun_out/${R}_per_image.json; tail -3 gpurun_out/${R}_per_image.err
