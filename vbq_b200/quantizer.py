@@ -151,8 +151,9 @@ class ChannelwisePriorCDFQuantizer:
             num_bits_dict[lamb] = nbs[i]
         return Z_hat_dict, num_bits_dict
 
-    def compress_latents(self, posterior_means, posterior_logvars, lambs):
-        """Reference quantizer.py:190-240.  sigma = sqrt(exp(logvar)) is computed inside the kernel."""
+    def _compress_latents_device(self, posterior_means, posterior_logvars, lambs):
+        """The device half of `compress_latents`: one kernel call for all lambdas; every result stays on the GPU as a
+        (len(lambs),) + latent-shape tensor."""
         C = int(posterior_logvars.shape[-1])
         assert C == self.num_channels
         if self.entropy_models is None:
@@ -163,33 +164,44 @@ class ChannelwisePriorCDFQuantizer:
         corrected = bool(self.raw_code_length_entropy_models)
         out = self.quantize(m, lv, lambs, logvar=True, entropy_bits=True,
                             outputs=ops.OUT_ZHAT | (ops.OUT_BITS if corrected else ops.OUT_LEVEL))
+        L = len(lambs)
+        return dict(Z_hat=out['zhat'].reshape((L,) + shape),
+                    raw_num_bits=(out['bits'] if corrected else out['level']).reshape((L,) + shape),
+                    num_bits=out['em_bits'].reshape((L,) + shape), corrected=corrected)
+
+    def _latents_to_host(self, dev_out, lambs):
         out_keys = ('Z_hat', 'raw_num_bits', 'num_bits_cl', 'num_bits')
         output = {key: dict() for key in out_keys}
         # one device-to-host copy per output tensor (the reference's np.reshape moves to the CPU, quantizer.py:237)
-        zs = utils.to_host_numpy(out['zhat'])
-        raws = utils.to_host_numpy(out['bits'] if corrected else out['level'])
-        ems = utils.to_host_numpy(out['em_bits'])
+        zs = utils.to_host_numpy(dev_out['Z_hat'])
+        raws = utils.to_host_numpy(dev_out['raw_num_bits'])
+        ems = utils.to_host_numpy(dev_out['num_bits'])
         for i, lamb in enumerate(lambs):
-            raw = raws[i].reshape(shape)
-            output['Z_hat'][lamb] = zs[i].reshape(shape)
-            output['raw_num_bits'][lamb] = raw
-            if corrected:
-                output['num_bits_cl'][lamb] = raw
-            output['num_bits'][lamb] = ems[i].reshape(shape)
+            output['Z_hat'][lamb] = zs[i]
+            output['raw_num_bits'][lamb] = raws[i]
+            if dev_out['corrected']:
+                output['num_bits_cl'][lamb] = raws[i]
+            output['num_bits'][lamb] = ems[i]
         return output
 
+    def compress_latents(self, posterior_means, posterior_logvars, lambs):
+        """Reference quantizer.py:190-240.  sigma = sqrt(exp(logvar)) is computed inside the kernel."""
+        return self._latents_to_host(self._compress_latents_device(posterior_means, posterior_logvars, lambs), lambs)
+
     def compress(self, X, vae, lambs, clip=True):
-        """Reference quantizer.py:242-256: encode, quantize for every lambda, decode the stacked Z_hat."""
+        """Reference quantizer.py:242-256: encode, quantize for every lambda, decode the stacked Z_hat.  The quantized
+        latents are handed to `vae.decode` on the device in the decoder's layout (len(lambs)*B, H', W', C) — no host
+        round trip between the search and the reconstruction."""
         posterior_means, posterior_logvars = vae.encode(X)
-        output = self.compress_latents(posterior_means, posterior_logvars, lambs)
-        Z_hat_dict = output['Z_hat']
-        Z_hat_batch = np.stack([Z_hat_dict[lamb] for lamb in lambs])          # len(lambs) by latent_shape
-        Z_hat_flat_batch = Z_hat_batch.reshape([-1, *posterior_means.shape[1:]])
-        decoded = vae.decode(torch.from_numpy(Z_hat_flat_batch).to(self.device))
-        decoded = decoded.detach().cpu().numpy() if isinstance(decoded, torch.Tensor) else np.asarray(decoded)
-        X_hat_batch = decoded.reshape([len(lambs), *X.shape])
+        dev_out = self._compress_latents_device(posterior_means, posterior_logvars, lambs)
+        Z_hat_flat_batch = dev_out['Z_hat'].reshape((-1,) + tuple(posterior_means.shape[1:]))
+        decoded = vae.decode(Z_hat_flat_batch)
+        if isinstance(decoded, torch.Tensor):
+            decoded = utils.to_host_numpy(decoded.detach().contiguous())
+        X_hat_batch = np.asarray(decoded).reshape([len(lambs), *X.shape])
         if clip:
             X_hat_batch = np.clip(X_hat_batch, 0, 1)
+        output = self._latents_to_host(dev_out, lambs)
         output['X_hat'] = {lamb: X_hat_batch[i] for i, lamb in enumerate(lambs)}
         return output
 

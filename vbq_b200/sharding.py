@@ -58,8 +58,10 @@ class ShardedQuantizer:
     def rd_sweep(self, local_means, local_scales, lambs, logvar=False, entropy_bits=False, flags=0):
         """Totals-only rate-distortion sweep over this rank's shard; returns the global (n_lambda, 4) totals."""
         from . import ops
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            flags |= ops.FLAG_RESERVE_SM      # leave an SM to NCCL kernels of neighbouring calls (DESIGN.md §5)
         out = self.quantizer.quantize(local_means, local_scales, lambs, logvar=logvar, outputs=ops.OUT_TOTALS,
-                                      flags=flags, entropy_bits=False)
+                                      flags=flags, entropy_bits=entropy_bits)
         return all_reduce_totals(out['totals'], self.group)
 
     def build_entropy_models_from_latents(self, local_means, local_logvars, lambs, add_n_smoothing):

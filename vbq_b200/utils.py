@@ -58,9 +58,6 @@ def to_host_numpy(t):
     return h.numpy()
 
 
-def lambda_key_list(lambs):
-    """The reference keys its dicts by the lambda objects themselves (quantizer.py:172,226)."""
-    return list(lambs)
 
 
 def batch_quantize_indep_dims(Z_shape, code_points, code_lengths, fun, lambs, backend=None, return_np=True,
