@@ -159,6 +159,17 @@ def test_embedding_path_against_notebook():
     assert mism <= tot // 20000 + 3
 
 
+def test_empirical_entropy_matches_notebook():
+    from vbq_b200.word_embeddings import empirical_entropy
+    from oracle import vbq_oracle as O
+    g = load("notebook_embeddings")
+    for i in range(3):
+        v = g["optima_%d" % i]
+        want = O.empirical_entropy(v)
+        assert abs(empirical_entropy(torch.from_numpy(v).cuda()) - want) <= 1e-9 * max(want, 1.0)
+        assert abs(empirical_entropy(v) - want) <= 1e-9 * max(want, 1.0)
+
+
 def test_embedding_f64_kernel_vs_oracle_large():
     """1.5 M coordinates (SURVEY §8d C1 statistics at half size): float64 kernel == exhaustive notebook restatement."""
     import vbq_b200

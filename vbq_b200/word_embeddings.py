@@ -21,6 +21,16 @@ def empirical_std(means):
     return float(torch.sqrt(torch.mean(m.double().reshape(-1) ** 2)))
 
 
+def empirical_entropy(values):
+    """ipynb:452-455: total_counts*log2(total_counts) - sum(counts*log2(counts)) over the distinct values, i.e. the
+    bit length of an ideal entropy code of the quantized coordinates.  Device tensors stay on the device."""
+    t = values if isinstance(values, torch.Tensor) else torch.as_tensor(np.asarray(values))
+    _, counts = torch.unique(t.reshape(-1), return_counts=True)
+    c = counts.double()
+    total = c.sum()
+    return float(total * torch.log2(total) - (c * torch.log2(c)).sum())
+
+
 class GaussianCodebook:
     """`codepoints` / `lengths` of the notebook (heap order, float64 / int64) plus the device tables."""
 
