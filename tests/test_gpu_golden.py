@@ -215,3 +215,41 @@ def test_generic_operator_equals_reference():
     k = np.argmax(s, axis=0)
     assert np.array_equal(Zh2[0.3], np.take_along_axis(Pb, k[None], 0)[0])
     assert np.array_equal(nb2[0.3], np.take_along_axis(Lb, k[None], 0)[0])
+
+
+def test_batched_evaluation_driver_equals_per_image_loop():
+    """evaluate_compression_quantizer (all images x all lambdas in one launch) reproduces the reference's per-image
+    loop (utils.py:535-553) run through `compress`: B, BPP, BPL, BPPCL."""
+    import vbq_b200
+    g = load("learned_c6_n10")
+    q = make_quantizer(g)
+    lambs = lambs_of(g)
+    q.raw_code_length_entropy_models = {l: g["rcl_%d" % i] for i, l in enumerate(lambs)}
+    q.entropy_models = {l: g["em_%d" % i] for i, l in enumerate(lambs)}
+    means, logvars = torch.from_numpy(g["means"]).cuda(), torch.from_numpy(g["logvars"]).cuda()
+    Nimg, Hl, Wl, C = means.shape
+
+    class VAE:
+        def __init__(self, sl=None):
+            self.sl = sl
+
+        def encode(self, X):
+            return (means, logvars) if self.sl is None else (means[self.sl], logvars[self.sl])
+
+        def decode(self, z):
+            m = 0.5 + 0.01 * z.mean(dim=-1, keepdim=True)
+            return m.repeat_interleave(16, 1).repeat_interleave(16, 2).repeat_interleave(3, 3)
+
+    X = np.zeros((Nimg, 16 * Hl, 16 * Wl, 3), dtype=np.float32)
+    res = vbq_b200.evaluate_compression_quantizer(q, VAE(), X, lambs, return_reconstructions=True)
+    assert res["B"].shape == (Nimg, len(lambs)) and res["reconstructions"].shape == (len(lambs),) + X.shape
+    npix = X.shape[1] * X.shape[2]
+    for n in range(Nimg):
+        tmp = q.compress(X[n:n + 1], VAE(slice(n, n + 1)), lambs, clip=True)
+        for m, l in enumerate(lambs):
+            nb = tmp["num_bits"][l][0]
+            assert np.isclose(res["B"][n, m], np.sum(nb, dtype=np.float64), rtol=1e-6)
+            assert np.isclose(res["BPP"][n, m], np.sum(nb, dtype=np.float64) / npix, rtol=1e-6)
+            assert np.isclose(res["BPL"][n, m], np.sum(nb, dtype=np.float64) / nb.size, rtol=1e-6)
+            assert np.isclose(res["BPPCL"][n, m], np.sum(tmp["num_bits_cl"][l][0], dtype=np.float64) / npix, rtol=1e-6)
+            assert np.allclose(res["reconstructions"][m, n], tmp["X_hat"][l][0], atol=1e-6)

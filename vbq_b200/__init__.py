@@ -11,6 +11,8 @@ from .quantizer import ChannelwisePriorCDFQuantizer                  # noqa: E40
 from .learned_prior import BMSHJ2018Prior                            # noqa: E402
 from .vae_models import StandardGaussianPrior, FactoredGaussianPrior, GaussianVAE   # noqa: E402
 from .word_embeddings import GaussianCodebook                        # noqa: E402
+from .evaluation import evaluate_compression_quantizer               # noqa: E402
 
 __all__ = ["ops", "utils", "sharding", "ChannelwisePriorCDFQuantizer", "BMSHJ2018Prior",
-           "StandardGaussianPrior", "FactoredGaussianPrior", "GaussianVAE", "GaussianCodebook"]
+           "StandardGaussianPrior", "FactoredGaussianPrior", "GaussianVAE", "GaussianCodebook",
+           "evaluate_compression_quantizer"]
