@@ -73,6 +73,8 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_quantize_kernel(const QArgs a
     const size_t lam_off = (size_t)lam * (size_t)a.lam_stride;
     // byte address of tree entry (n, i) of this thread's channel = pb + V + entry_of(n,0)*64, V = 64*i + 32
     const char *pb = reinterpret_cast<const char *>(sT) + col * 4 - 32;
+    const int pbi = (int)__cvta_generic_to_shared(pb);   // the same base as a 32-bit shared-memory address
+    const int one = a.one, two = a.two;
     const float *sTc = sT + col;
     const float *sLenc = sLen + col;
 
@@ -220,11 +222,12 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_quantize_kernel(const QArgs a
                 float zp[U], zn[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const char *pa = pb + V[u];
-                    zp[u] = lds_f32(pa, imm);
+                    // integer multiply-adds with runtime factors 1 and 2: IMAD on the FMA pipe, not IADD3 on the ALU pipe
+                    const int pa = imad(V[u], one, pbi);
+                    zp[u] = lds_u32((unsigned)(pa + imm));
                     const int s = mu[u] > zp[u] ? 32 : -32;
-                    zn[u] = lds_f32(pa + 2 * s, imm);   // the other end of the bracket (pads at the edges)
-                    V[u] = 2 * V[u] + s;
+                    zn[u] = lds_u32((unsigned)(imad(s, two, pa) + imm));   // the other bracket end (pads at the edges)
+                    V[u] = imad(V[u], two, s);
                 }
 #pragma unroll
                 for (int k = 0; k < P; ++k) {
