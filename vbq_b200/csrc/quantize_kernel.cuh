@@ -2,6 +2,8 @@
 // Included by one translation unit per scoring mode (quantize_strict.cu, quantize_reference.cu, quantize_fast.cu) so
 // that nvcc can compile the modes in parallel.  See quantize.cu for the design notes.
 #pragma once
+#include <stdlib.h>
+
 #include "tree.cuh"
 
 // Scoring modes.  All three produce the reference's result; they differ in how much work proves it.
@@ -459,5 +461,10 @@ static int launch_mode2(const QArgs &a, int dev, int sms, cudaStream_t st) {
 template <int MODE>
 static int launch_quantize_mode(const QArgs &a, int dev, int sms, cudaStream_t st) {
     const bool prune = !(a.flags & VBQ_FLAG_NO_PRUNE);
+    if (MODE == kModeStrict && !prune) {   // development override (read once): VBQ_TUNE=<threads/128>
+        static const int tune = getenv("VBQ_TUNE") ? atoi(getenv("VBQ_TUNE")) : 4;
+        if (tune == 5) return launch_mode2<MODE, false, 2, 640>(a, dev, sms, st);
+        if (tune == 6) return launch_mode2<MODE, false, 2, 768>(a, dev, sms, st);
+    }
     return prune ? launch_mode2<MODE, true, 2, 512>(a, dev, sms, st) : launch_mode2<MODE, false, 2, 512>(a, dev, sms, st);
 }
