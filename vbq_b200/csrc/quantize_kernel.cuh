@@ -460,11 +460,7 @@ static int launch_mode2(const QArgs &a, int dev, int sms, cudaStream_t st) {
 // entry point of one scoring mode (defined by the translation unit that includes this header)
 template <int MODE>
 static int launch_quantize_mode(const QArgs &a, int dev, int sms, cudaStream_t st) {
+    // 640 threads (20 warps, <= 102 registers): measured best of 512 / 640 / 768 for the strict kernel
     const bool prune = !(a.flags & VBQ_FLAG_NO_PRUNE);
-    if (MODE == kModeStrict && !prune) {   // development override (read once): VBQ_TUNE=<threads/128>
-        static const int tune = getenv("VBQ_TUNE") ? atoi(getenv("VBQ_TUNE")) : 4;
-        if (tune == 5) return launch_mode2<MODE, false, 2, 640>(a, dev, sms, st);
-        if (tune == 6) return launch_mode2<MODE, false, 2, 768>(a, dev, sms, st);
-    }
-    return prune ? launch_mode2<MODE, true, 2, 512>(a, dev, sms, st) : launch_mode2<MODE, false, 2, 512>(a, dev, sms, st);
+    return prune ? launch_mode2<MODE, true, 2, 640>(a, dev, sms, st) : launch_mode2<MODE, false, 2, 640>(a, dev, sms, st);
 }
