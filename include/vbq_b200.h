@@ -55,6 +55,8 @@ enum {
 #define VBQ_FLAG_NO_PRUNE 2u     /* visit every bit depth even when deeper levels provably cannot win */
 #define VBQ_FLAG_RESERVE_SM 64u       /* launch one CTA fewer than there are SMs, so that a concurrent kernel on another
                                          stream (e.g. the NCCL all-reduce of the previous call's totals) finds a free SM */
+#define VBQ_FLAG_BRACKET_WALK 128u     /* single lambda: use the nearer-bracket-end walk (strict mode) even where the
+                                         certified bisection kernel applies (same results; for comparison) */
 #define VBQ_FLAG_REFERENCE_WALK 32u   /* score both bracket ends of every depth (the slower, literal formulation; same results) */
 #define VBQ_FLAG_NO_SWEEP 16u         /* walk the tree once per lambda instead of once for all lambdas */
 #define VBQ_FLAG_ACCUMULATE_TOTALS 8u /* add this call's sums to d_totals instead of overwriting them */

@@ -288,3 +288,61 @@ def test_garbage_inputs_stay_in_bounds(flags):
         srt = q.code_points_by_channel.cpu().numpy()
         for i in range(len(lambs)):
             assert np.array_equal(np.take_along_axis(srt.T, qi[i].astype(np.int64), axis=0), out["zhat"][i].cpu().numpy())
+
+
+@pytest.mark.parametrize("N,C,rows", [(10, 48, 20000), (10, 5, 777), (6, 17, 3000), (4, 33, 257), (1, 3, 40), (0, 2, 40)])
+def test_bisection_equals_reference_walk(N, C, rows):
+    """The default single-lambda kernel (certified bisection: one path node per depth, approximate ranking with a
+    guard band, literal search for uncertified coordinates) vs VBQ_FLAG_REFERENCE_WALK and the round-1 bracket walk
+    (VBQ_FLAG_BRACKET_WALK): identical outputs for every lambda, prune on and off; totals within 1e-6."""
+    import vbq_b200
+    from vbq_b200 import ops
+    pr = H.make_prior(C, seed=300 + N)
+    q = vbq_b200.ChannelwisePriorCDFQuantizer(C, N)
+    q.set_code_points(ops.build_code_points_learned(_dev(pr.packed()), N))
+    table = q.all_code_points.cpu().numpy()
+    mu, sigma, _ = H.make_latents(pr, rows, 41 + N, table=table)
+    rng = np.random.default_rng(9)
+    # a third of the coordinates sit within a few ulps of code points / of bracket midpoints: near-ties in bulk
+    srt = q.code_points_by_channel.cpu().numpy()
+    idx = rng.integers(0, srt.shape[1], (rows, C))
+    on = srt[np.arange(C)[None, :], idx]
+    nxt = srt[np.arange(C)[None, :], np.minimum(idx + 1, srt.shape[1] - 1)]
+    pick = rng.integers(0, 6, (rows, C))
+    mu = np.where(pick == 0, on, np.where(pick == 1, (0.5 * (on.astype(np.float64) + nxt)).astype(np.float32), mu))
+    mu = mu.astype(np.float32)
+    outs = ops.OUT_ZHAT | ops.OUT_QIDX | ops.OUT_LEVEL | ops.OUT_BITS | ops.OUT_TOTALS
+    for lamb in (0.0, 1e-30, 2.0 ** -8, 0.1, 0.5, 3.0, 16.0, 1e4):
+        for extra in (0, ops.FLAG_NO_PRUNE):
+            a = q.quantize(_dev(mu), _dev(sigma), [lamb], outputs=outs, flags=extra)
+            b = q.quantize(_dev(mu), _dev(sigma), [lamb], outputs=outs, flags=extra | ops.FLAG_REFERENCE_WALK)
+            c = q.quantize(_dev(mu), _dev(sigma), [lamb], outputs=outs, flags=extra | ops.FLAG_BRACKET_WALK)
+            for k in ("zhat", "qidx", "level", "bits"):
+                assert torch.equal(a[k], b[k]), (lamb, extra, k)
+                assert torch.equal(a[k], c[k]), (lamb, extra, k)
+            assert torch.equal(a["totals"][:, :2], b["totals"][:, :2])
+            assert torch.allclose(a["totals"][:, 3], b["totals"][:, 3], rtol=1e-6, atol=1e-9)
+
+
+def test_bisection_rejects_non_monotone_penalties():
+    """Penalties that are not non-decreasing in depth void the one-candidate-per-depth argument; the kernel detects
+    them while staging and sends every coordinate through the literal search.  Checked through the raw C ABI with a
+    decreasing penalty table against VBQ_FLAG_REFERENCE_WALK."""
+    import vbq_b200
+    from vbq_b200 import ops
+    C, N, rows = 16, 10, 4096
+    pr = H.make_prior(C, seed=12)
+    q = vbq_b200.ChannelwisePriorCDFQuantizer(C, N)
+    q.set_code_points(ops.build_code_points_learned(_dev(pr.packed()), N))
+    mu, sigma, _ = H.make_latents(pr, rows, 13, table=q.all_code_points.cpu().numpy())
+    rng = np.random.default_rng(2)
+    pen = _dev(rng.uniform(0.0, 3.0, (1, 1, N + 1)).astype(np.float32))
+    res = []
+    for fl in (ops.FLAG_NO_PRUNE, ops.FLAG_NO_PRUNE | ops.FLAG_REFERENCE_WALK, 0):
+        z = torch.empty((1, rows, C), dtype=torch.float32, device="cuda")
+        lv = torch.empty((1, rows, C), dtype=torch.int32, device="cuda")
+        ops.quantize_into(_dev(mu), _dev(sigma), q.all_code_points, q._packed, pen, None, None, N, zhat=z, level=lv,
+                          flags=fl)
+        res.append((z, lv))
+    for z, lv in res[1:]:
+        assert torch.equal(z, res[0][0]) and torch.equal(lv, res[0][1])

@@ -98,7 +98,7 @@ extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long r
                         n_lambda, pen_channels);
     RETURN_IF(vbq_check_depth(N));
     if (flags & ~(VBQ_FLAG_LOGVAR | VBQ_FLAG_NO_PRUNE | VBQ_FLAG_FAST | VBQ_FLAG_ACCUMULATE_TOTALS | VBQ_FLAG_NO_SWEEP |
-                  VBQ_FLAG_REFERENCE_WALK | VBQ_FLAG_RESERVE_SM))
+                  VBQ_FLAG_REFERENCE_WALK | VBQ_FLAG_RESERVE_SM | VBQ_FLAG_BRACKET_WALK))
         return vbq_fail(VBQ_ERR_BAD_FLAGS, "vbq_quantize: unknown flag bits 0x%x", flags);
     if (!d_table || !d_packed || !d_penalty || (rows > 0 && (!d_mu || !d_sigma)))
         return vbq_fail(VBQ_ERR_NULL_POINTER, "vbq_quantize: null input pointer");
@@ -168,7 +168,11 @@ extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long r
         }
         if (flags & VBQ_FLAG_FAST) st_ = vbq_launch_quantize_fast(b, dev, sms, st);
         else if (flags & VBQ_FLAG_REFERENCE_WALK) st_ = vbq_launch_quantize_reference(b, dev, sms, st);
-        else st_ = vbq_launch_quantize_strict(b, dev, sms, st);
+        else {
+            // default: certified bisection (raw code lengths, N <= 10); otherwise the bracket walk in strict mode
+            st_ = (flags & VBQ_FLAG_BRACKET_WALK) ? -1 : vbq_launch_quantize_bisect(b, dev, sms, st);
+            if (st_ < 0) st_ = vbq_launch_quantize_strict(b, dev, sms, st);
+        }
         RETURN_IF(st_);
     }
     return VBQ_OK;

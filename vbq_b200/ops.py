@@ -24,6 +24,7 @@ FLAG_FAST = _lib.FLAG_FAST
 FLAG_NO_SWEEP = _lib.FLAG_NO_SWEEP
 FLAG_REFERENCE_WALK = _lib.FLAG_REFERENCE_WALK
 FLAG_RESERVE_SM = _lib.FLAG_RESERVE_SM
+FLAG_BRACKET_WALK = _lib.FLAG_BRACKET_WALK
 
 
 def _ptr(t: Optional[torch.Tensor]):
