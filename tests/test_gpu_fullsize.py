@@ -83,7 +83,7 @@ def test_kodak_full_size_properties():
         tot += o["totals"][0]
     assert torch.equal(torch.cat(parts), sweep["qidx"][8])
     single8 = q.quantize(mu, sigma, [lambs[8]], outputs=outs)["totals"][0]
-    assert torch.allclose(tot, single8, rtol=1e-12)                 # same kernel: only the float64 reduction order differs
+    assert torch.allclose(tot, single8, rtol=1e-9)                  # same kernel: only the pairing of float32 terms and the float64 reduction order differ
     assert torch.allclose(tot, sweep["totals"][8], rtol=1e-6)       # sweep kernel: float32 distortion terms rounded differently
     # oracle on a random sample of rows (same table): bit-exact
     idx = torch.randperm(rows, device=DEV)[:300]

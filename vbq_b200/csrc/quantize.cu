@@ -119,6 +119,7 @@ extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long r
     a.flags = flags;
     a.one = 1;
     a.two = 2;
+    a.keymask = 0xfffffff0u;
     a.outm = (d_zhat ? 1u : 0u) | (d_qidx ? 2u : 0u) | (d_level ? 4u : 0u) | (d_bits ? 8u : 0u) |
              (d_em_bits ? 16u : 0u) | (d_entropy_model ? 32u : 0u) | (d_length ? 64u : 0u);
     a.n_groups = (C + VBQ_GROUP - 1) / VBQ_GROUP;
