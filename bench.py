@@ -262,34 +262,41 @@ def run_ours(args, rank, world, local_rank):
     # rotating buffer sets so that no step finds its inputs in the 126 MB L2
     set_bytes = COORDS * BYTES_PER_COORD
     n_sets = max(3, -(-3 * L2_BYTES // set_bytes))
+    if os.environ.get("VBQ_SETS"):            # development only: 1 = inputs stay in L2 (NOT a valid bench line)
+        n_sets = int(os.environ["VBQ_SETS"])
     sets = []
     for s in range(n_sets):
         mu, sigma = make_batch(prior, 1000 + 17 * rank + s, dev)
         sets.append(dict(mu=mu, sigma=sigma,
                          qidx=torch.empty((1, ROWS, C), dtype=torch.int32, device=dev),
                          bits=torch.empty((1, ROWS, C), dtype=torch.float32, device=dev)))
-    # per-step totals live in a small ring so that the NCCL all-reduce of step i (asynchronous, on NCCL's own
-    # stream) overlaps the kernel of step i+1; all pending reductions are waited for inside the timed region
-    n_ring = 8
-    totals_ring = [torch.zeros((1, 4), dtype=torch.float64, device=dev) for _ in range(n_ring)]
-    totals = totals_ring[0]
-    ws = ops.quantize_workspace(1, dev)
-    pending = []
+    # one captured plan per buffer set: a step is one cudaGraphLaunch of the vbq_quantize call (kernel + totals); the
+    # NCCL all-reduce of step i (asynchronous, on NCCL's own stream) overlaps the kernel of step i+1, and a set is
+    # reused only after the all-reduce of its previous totals has finished (all inside the timed region)
+    plans = []
+    for b in sets:
+        b["totals"] = torch.zeros((1, 4), dtype=torch.float64, device=dev)
+        plans.append(ops.QuantizePlan(b["mu"], b["sigma"], q.all_code_points, q._packed, pen, length, None, N_BITS,
+                                      qidx=b["qidx"], bits=b["bits"], totals=b["totals"], flags=args.flags,
+                                      graph=not args.no_graph))
+    totals = sets[0]["totals"]
+    pending = [None] * n_sets
 
     def step(i):
-        b = sets[i % n_sets]
-        t = totals_ring[i % n_ring]
-        if world > 1 and len(pending) >= n_ring - 1:
-            pending.pop(0).wait()
-        ops.quantize_into(b["mu"], b["sigma"], q.all_code_points, q._packed, pen, length, None, N_BITS,
-                          qidx=b["qidx"], bits=b["bits"], totals=t, workspace=ws, flags=args.flags)
+        s_ = i % n_sets
+        if pending[s_] is not None:
+            pending[s_].wait()
+            pending[s_] = None
+        t = plans[s_].run()
         if world > 1:
-            pending.append(dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True))
+            pending[s_] = dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)
         return t
 
     def drain():
-        while pending:
-            pending.pop(0).wait()
+        for s_ in range(n_sets):
+            if pending[s_] is not None:
+                pending[s_].wait()
+                pending[s_] = None
 
     def barrier():
         if world > 1:
@@ -300,17 +307,19 @@ def run_ours(args, rank, world, local_rank):
         step(i)
     drain()
     barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     with ClockSampler(local_rank) as clocks:
         barrier()
         ev[0].record()
         for i in range(args.steps):
             step(args.warmup + i)
-            ev[i + 1].record()
         drain()
+        ev[1].record()
         barrier()
-    total_ms = ev[0].elapsed_time(ev[-1])
-    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = ev[0].elapsed_time(ev[1])
+    # average launch duration of the kernel over the timed region (launch gaps included): the steps are back to back
+    # on one stream and each step is exactly one launch of the quantize kernel
+    per_launch_ms = [total_ms / args.steps]
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -320,8 +329,8 @@ def run_ours(args, rank, world, local_rank):
     # end-to-end through the C-ABI host entry point (vbq_quantize_host, what the reference-facing
     # compress_batch_channel_latents runs for host arrays): HOST pinned buffers in, HOST pinned buffers out, the
     # upload / kernel / download of row chunks overlapped on three streams, all inside the timed region.
-    h_mu = [b["mu"].cpu().pin_memory() for b in sets[:2]]
-    h_sigma = [b["sigma"].cpu().pin_memory() for b in sets[:2]]
+    h_mu = [b["mu"].cpu().pin_memory() for b in (sets * 2)[:2]]
+    h_sigma = [b["sigma"].cpu().pin_memory() for b in (sets * 2)[:2]]
     h_q = torch.empty((1, ROWS, C), dtype=torch.int32).pin_memory()
     h_b = torch.empty((1, ROWS, C), dtype=torch.float32).pin_memory()
     h_tot = torch.empty((1, 4), dtype=torch.float64).pin_memory()
@@ -409,6 +418,7 @@ def main():
     ap.add_argument("--chunk-rows", type=int, default=9216, help="rows per chunk of the host pipeline (e2e leg)")
     ap.add_argument("--no-reserve", action="store_true", help="multi-GPU: do not leave an SM to the NCCL kernel")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="launch every step eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

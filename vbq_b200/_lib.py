@@ -18,6 +18,7 @@ FLAG_NO_SWEEP = 16
 FLAG_REFERENCE_WALK = 32
 FLAG_RESERVE_SM = 64
 FLAG_BRACKET_WALK = 128
+FLAG_WORKSPACE_ZEROED = 256
 GROUP = 16
 TOTALS = 4
 PRIOR_PARAMS = 43

@@ -87,6 +87,7 @@ extern "C" int vbq_host_ctx_create(int C, int N, int n_lambda, long long chunk_r
     if (outputs & VBQ_OUT_TOTALS) {
         c->ws_bytes = vbq_quantize_workspace_bytes(n_lambda);
         CTX_TRY(cudaMalloc(&c->d_ws, (size_t)c->ws_bytes));
+        CTX_TRY(cudaMemset(c->d_ws, 0, (size_t)c->ws_bytes));   // every call leaves the ticket counters zero again
         CTX_TRY(cudaMalloc(&c->d_totals, (size_t)n_lambda * VBQ_TOTALS * sizeof(double)));
     }
     *out = c;
@@ -130,7 +131,8 @@ extern "C" int vbq_quantize_host(vbq_host_ctx *c, const float *h_mu, const float
                                d_entropy_model, h_zhat ? s.zhat : nullptr, h_qidx ? s.qidx : nullptr,
                                h_level ? s.level : nullptr, h_bits ? s.bits : nullptr,
                                h_em_bits ? s.em_bits : nullptr, h_totals ? c->d_totals : nullptr, c->d_ws, c->ws_bytes,
-                               flags | (h_totals && k > 0 ? VBQ_FLAG_ACCUMULATE_TOTALS : 0u), c->s_k));
+                               flags | VBQ_FLAG_WORKSPACE_ZEROED | (h_totals && k > 0 ? VBQ_FLAG_ACCUMULATE_TOTALS : 0u),
+                               c->s_k));
         CUDA_TRY(cudaEventRecord(s.done, c->s_k));
         // download: (n_lambda, nr, C) device block -> rows [r0, r0+nr) of each lambda plane of the host array
         CUDA_TRY(cudaStreamWaitEvent(c->s_out, s.done, 0));

@@ -98,7 +98,7 @@ extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long r
                         n_lambda, pen_channels);
     RETURN_IF(vbq_check_depth(N));
     if (flags & ~(VBQ_FLAG_LOGVAR | VBQ_FLAG_NO_PRUNE | VBQ_FLAG_FAST | VBQ_FLAG_ACCUMULATE_TOTALS | VBQ_FLAG_NO_SWEEP |
-                  VBQ_FLAG_REFERENCE_WALK | VBQ_FLAG_RESERVE_SM | VBQ_FLAG_BRACKET_WALK))
+                  VBQ_FLAG_REFERENCE_WALK | VBQ_FLAG_RESERVE_SM | VBQ_FLAG_BRACKET_WALK | VBQ_FLAG_WORKSPACE_ZEROED))
         return vbq_fail(VBQ_ERR_BAD_FLAGS, "vbq_quantize: unknown flag bits 0x%x", flags);
     if (!d_table || !d_packed || !d_penalty || (rows > 0 && (!d_mu || !d_sigma)))
         return vbq_fail(VBQ_ERR_NULL_POINTER, "vbq_quantize: null input pointer");
@@ -133,7 +133,8 @@ extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long r
             return vbq_fail(VBQ_ERR_MISALIGNED, "vbq_quantize: workspace not 256-byte aligned");
         a.ticket = (unsigned *)d_workspace;
         a.partials = (double *)((char *)d_workspace + ticket_bytes(n_lambda));
-        CUDA_TRY(cudaMemsetAsync(a.ticket, 0, (size_t)n_lambda * sizeof(unsigned), st));
+        if (!(flags & VBQ_FLAG_WORKSPACE_ZEROED))
+            CUDA_TRY(cudaMemsetAsync(a.ticket, 0, (size_t)n_lambda * sizeof(unsigned), st));
     }
     if (rows == 0) {
         if (d_totals) CUDA_TRY(cudaMemsetAsync(d_totals, 0, (size_t)n_lambda * VBQ_TOTALS * sizeof(double), st));

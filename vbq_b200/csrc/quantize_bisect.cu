@@ -73,58 +73,82 @@ __device__ __forceinline__ unsigned make_key(float loss, unsigned mask) {
     return k;
 }
 
+// Work decomposition.  A TILE is 4 consecutive rows x the 16 channels of one group: one warp iteration (lane =
+// (row parity, channel), two coordinates per thread: rows 2u + parity, u = 0, 1).  The tiles of a launch, ordered by
+// (group, row), are cut into one contiguous span per CTA; inside a span the warps of the CTA CLAIM tiles from a
+// shared-memory counter, kStages-1 tiles ahead of the one they compute (claim -> cp.async -> compute), so that all
+// warps of a CTA finish within one tile of each other whatever the scheduler's warp priorities were.  A CTA whose
+// span crosses a group boundary loads a second tree; the cut positions charge kSwitchTiles tiles for that.
+constexpr int kTileRows = 4;
+constexpr int kTileFloats = 2 * kTileRows * VBQ_GROUP;   // mu rows then sigma rows: [2][4][16]
+constexpr int kSwitchTiles = 32;
+
+// first real tile (in group-major order) of virtual position v: every group is preceded by kSwitchTiles virtual tiles
+__device__ __forceinline__ long long span_cut(long long v, long long tiles_per_group, int n_groups) {
+    const long long vg = tiles_per_group + kSwitchTiles;
+    const long long g = min(v / vg, (long long)n_groups);
+    const long long o = v - g * vg;
+    return g * tiles_per_group + max(0ll, o - kSwitchTiles);
+}
+
 // NT > 0: max_bits_per_coord == NT at compile time; NT == 0: runtime depth (<= kSmemDepth).
 // OUT >= 0: the set of requested outputs (bit 0 zhat, 1 qidx, 2 level, 3 bits) is known at compile time; OUT < 0: runtime.
-// VEC: C % 4 == 0 and 16-byte aligned latents: every warp stages its own 2U rows x 16 channels of mu and sigma with ONE
-// 16-byte cp.async per lane and iteration (a 512-byte tile per warp) instead of four 4-byte copies per thread.
-template <bool PRUNE, bool TOTALS, int NT, int OUT, bool VEC, int U, int kThreads>
+// VEC: C % 4 == 0 and 16-byte aligned latents: a warp stages its tile (256 B of mu, 256 B of sigma) with ONE 16-byte
+// cp.async per lane; otherwise every thread copies its own two coordinates with 4-byte cp.async.
+template <bool PRUNE, bool TOTALS, int NT, int OUT, bool VEC, int kThreads>
 __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) {
-    static_assert(U % 2 == 0, "coordinates are processed in f32x2 pairs");
-    static_assert(!VEC || U == 2, "the per-warp tile of the vectorised staging is one 16-byte chunk per lane");
-    constexpr int RP = kThreads / VBQ_GROUP;              // rows covered by one pass of the CTA
-    constexpr int P = U / 2;
+    constexpr int U = 2, P = 1;
+    constexpr int kWarps = kThreads / 32;
     extern __shared__ __align__(16) float smem[];
     float *sT = smem;                                   // [kPadEntries][16] code points of depths 0..10
     float *sPen = sT + kPadEntries * VBQ_GROUP;         // [kSmemDepth+1][16] penalties (+inf beyond N)
-    // staging ring, kStages deep.  !VEC: [kStages][2][U][kThreads], thread-private slots.
-    // VEC: per warp [kStages][2 arrays][2U rows][16 channels]; consumer (col, rsub&1) reads row u*2 + (rsub&1)
-    float *sStage = sPen + (kSmemDepth + 1) * VBQ_GROUP;
-    float *myStage = VEC ? sStage + (threadIdx.x >> 5) * (kStages * 4 * U * VBQ_GROUP) + (threadIdx.x & 31)
-                         : sStage + threadIdx.x;
-    constexpr int kSlotStride = VEC ? 4 * U * VBQ_GROUP : 2 * U * kThreads;   // floats per ring slot
-    constexpr int kArrStride = VEC ? 2 * U * VBQ_GROUP : U * kThreads;        // mu -> sigma
-    constexpr int kRowStride = VEC ? 2 * VBQ_GROUP : kThreads;               // u -> u + 1
+    float *sStage = sPen + (kSmemDepth + 1) * VBQ_GROUP;   // [kWarps][kStages][kTileFloats] staging rings
     __shared__ double sRed[VBQ_TOTALS][kMaxThreads / 32];
     __shared__ unsigned sGuard[VBQ_GROUP];
+    __shared__ int sNext;                               // next unclaimed tile of the current segment
     __shared__ bool sLast;
 
     const int N = NT > 0 ? NT : a.N;
     const int lam = blockIdx.y;
     const unsigned outm = OUT >= 0 ? (unsigned)OUT : (a.outm & 15u);
-    const int col = threadIdx.x & (VBQ_GROUP - 1);
-    const int rsub = threadIdx.x >> 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = lane & (VBQ_GROUP - 1);
+    const int par = lane >> 4;                          // row parity inside the tile
     const bool logvar = (a.flags & VBQ_FLAG_LOGVAR) != 0;
-    const long long u0 = a.total_units * blockIdx.x / gridDim.x;
-    const long long u1 = a.total_units * (blockIdx.x + 1) / gridDim.x;
     const int C = a.C;
     const int rows = (int)a.rows;                       // the host splits calls so that rows*C < 2^29
+    const long long tpg = a.passes;                     // tiles per group = ceil(rows / 4)
+    const long long vtotal = (tpg + kSwitchTiles) * a.n_groups;
+    const long long u0 = span_cut(vtotal * blockIdx.x / gridDim.x, tpg, a.n_groups);
+    const long long u1 = span_cut(vtotal * (blockIdx.x + 1) / gridDim.x, tpg, a.n_groups);
     const size_t lam_off = (size_t)lam * (size_t)a.lam_stride;
     // shared-memory byte address of padded entry (n, i) of this thread's channel = pbi + 64*K + 128*n, K = 2^n + i
     // (entry_of(n, i) = K + 2n): K is the 1-based heap index of the node, children 2K and 2K+1
     const int pbi = (int)__cvta_generic_to_shared(sT + col);
     const float *sTc = sT + col;
     const unsigned kmask = a.keymask;                   // 0xfffffff0 as a runtime value: stays in one register
+    float *wStage = sStage + warp * (kStages * kTileFloats);
+    const float *myStage = wStage + par * VBQ_GROUP + col;   // + slot*kTileFloats + arr*64 + u*32
 
     double acc_dist = 0.0;
     int acc_level = 0;   // < 2^31: at most 2^29 coordinates per launch, depth <= 10
+#ifdef VBQ_TRACE
+    unsigned long long tr_t0 = 0, tr_t1 = 0, tr_t2 = 0;
+    int tr_segs = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t0));
+    const long long tr_c0 = clock64();
+#endif
 
     long long unit = u0;
     while (unit < u1) {
-        // ---- segment: a run of row passes inside one 16-channel group --------------------------------------
-        const int g = (int)(unit / a.passes);
-        const int p0 = (int)(unit - (long long)g * a.passes);
-        const int p1 = (int)min(a.passes, (long long)p0 + (u1 - unit));
-        unit += p1 - p0;
+#ifdef VBQ_TRACE
+        ++tr_segs;
+#endif
+        // ---- segment: a run of tiles inside one 16-channel group -----------------------------------------------
+        const int g = (int)(unit / tpg);
+        const int t0 = (int)(unit - (long long)g * tpg);
+        const int n_tiles = (int)min(tpg - t0, u1 - unit);   // tiles t0 .. t0 + n_tiles - 1 of group g
+        unit += n_tiles;
 
         __syncthreads();
         {
@@ -145,87 +169,82 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
                 }
                 sGuard[j] = mono ? kKeyGuard : 0xffffffffu;   // 0xffffffff: every coordinate takes the slow path
             }
+            if (threadIdx.x == 0) sNext = 0;
         }
         __syncthreads();
 
         const int c = g * VBQ_GROUP + col;
         const bool c_ok = c < C;
         const int cc = min(c, C - 1);
-        const float *mu_c = a.mu + cc, *sg_c = a.sigma + cc;      // element (row, channel) = base[row * C]
-        float *zhat_c = a.zhat ? a.zhat + lam_off + cc : nullptr;
-        int *qidx_c = a.qidx ? a.qidx + lam_off + cc : nullptr;
-        int *level_c = a.level ? a.level + lam_off + cc : nullptr;
-        float *bits_c = a.bits ? a.bits + lam_off + cc : nullptr;
+        // element offset of this thread's first coordinate inside tile 0 of the segment; tile j adds j * 4C
+        const unsigned thr_off = (unsigned)(t0 * kTileRows + par) * (unsigned)C + (unsigned)cc;
+        const unsigned tile_step = (unsigned)(kTileRows * C), u_step = (unsigned)(2 * C);
+        const int seg_row0 = t0 * kTileRows;
+        float *zhat_c = a.zhat ? a.zhat + lam_off : nullptr;
+        int *qidx_c = a.qidx ? a.qidx + lam_off : nullptr;
+        int *level_c = a.level ? a.level + lam_off : nullptr;
+        float *bits_c = a.bits ? a.bits + lam_off : nullptr;
         float pen[kSmemDepth + 1];
 #pragma unroll
         for (int n = 0; n <= kSmemDepth; ++n) pen[n] = sPen[n * VBQ_GROUP + col];
         const unsigned guard = sGuard[col];
         const float z0 = sTc[entry_of(0, 0) * VBQ_GROUP];
+        // tiles below full_tiles have all 4 rows inside the matrix; a group with 16 real channels needs no predicates
+        const bool group_full = g * VBQ_GROUP + VBQ_GROUP <= C;
+        const int full_tiles = group_full ? min(n_tiles, (rows - seg_row0) / kTileRows) : 0;
 
-        const int row_end = c_ok ? min(p1 * RP, rows) : 0;   // threads of channels >= C never pass the row test
-        // a full iteration (all U row passes inside the matrix, all 16 channels of the group real) needs no predicates
-        const int full_rows = (g * VBQ_GROUP + VBQ_GROUP <= C) ? min(p1 * RP, rows) : 0;
-        int row = p0 * RP + rsub;
-        unsigned off = (unsigned)row * (unsigned)C;          // element offset of row `row`
-        const unsigned off_step = (unsigned)(RP * C);
-
-        // stage kStages-1 iterations ahead; every iteration commits exactly one group (possibly empty)
-        // VEC producer role of this lane: array (lane>>4), tile row ((lane>>2)&3) = u*2 + r, 16-byte chunk (lane&3)
-        const int lane = threadIdx.x & 31;
-        const int prod_row = 2 * (threadIdx.x >> 5) + ((lane >> 2) & 1) + ((lane >> 3) & 1) * RP;   // row inside a CTA iteration
-        const int prod_col = g * VBQ_GROUP + (lane & 3) * 4;
-        const float *prod_src = nullptr;   // advanced by one CTA iteration per stage_rows call
-        float *prod_dst = nullptr;
-        int prod_limit = 0;
-        if (VEC) {
-            prod_src = ((lane >> 4) ? a.sigma : a.mu) + ((size_t)(p0 * RP + prod_row) * C + prod_col);
-            prod_dst = myStage - lane + (lane >> 4) * kArrStride + ((lane >> 2) & 3) * VBQ_GROUP + (lane & 3) * 4;
-            prod_limit = prod_col < C ? min(p1 * RP, rows) : 0;
-        }
-        const size_t it_step = (size_t)U * off_step;
-        auto stage_rows = [&](int it_row, unsigned it_off, int slot) {
-            const bool full = it_row - rsub + U * RP <= full_rows;       // CTA-uniform
-            if (VEC) {
-                if (full || it_row - rsub + prod_row < prod_limit) cp_async_16(prod_dst + slot * kSlotStride, prod_src);
-                prod_src += it_step;
-            } else if (full) {
+        // producer role of this lane.  VEC: array (lane>>4), tile row ((lane>>2)&3), 16-byte chunk (lane&3)
+        const int prod_row = VEC ? ((lane >> 2) & 3) : par;
+        const int prod_col = VEC ? g * VBQ_GROUP + (lane & 3) * 4 : cc;
+        const float *prod_src = ((VEC && (lane >> 4)) ? a.sigma : a.mu) + ((size_t)(seg_row0 + prod_row) * C + prod_col);
+        float *prod_dst = VEC ? wStage + (lane >> 4) * (kTileRows * VBQ_GROUP) + prod_row * VBQ_GROUP + (lane & 3) * 4
+                              : wStage + par * VBQ_GROUP + col;
+        const bool prod_col_ok = VEC ? prod_col < C : c_ok;
+        auto claim = [&]() -> int {
+            int j = 0;
+            if (lane == 0) j = atomicAdd(&sNext, 1);
+            return __shfl_sync(0xffffffffu, j, 0);
+        };
+        auto stage = [&](int j, int slot) {   // every call commits exactly one group (possibly empty)
+            if (j < n_tiles) {
+                const float *src = prod_src + (size_t)j * tile_step;
+                float *dst = prod_dst + slot * kTileFloats;
+                if (VEC) {
+                    if (j < full_tiles || (prod_col_ok && seg_row0 + j * kTileRows + prod_row < rows)) cp_async_16(dst, src);
+                } else {
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    cp_async_f32_idx(myStage + slot * kSlotStride + u * kRowStride, mu_c, it_off + u * off_step);
-                    cp_async_f32_idx(myStage + slot * kSlotStride + kArrStride + u * kRowStride, sg_c, it_off + u * off_step);
-                }
-            } else {
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (it_row + u * RP < row_end) {
-                        cp_async_f32_idx(myStage + slot * kSlotStride + u * kRowStride, mu_c, it_off + u * off_step);
-                        cp_async_f32_idx(myStage + slot * kSlotStride + kArrStride + u * kRowStride, sg_c, it_off + u * off_step);
+                    for (int u = 0; u < U; ++u) {
+                        if (j < full_tiles || (prod_col_ok && seg_row0 + j * kTileRows + 2 * u + par < rows)) {
+                            cp_async_f32(dst + u * 2 * VBQ_GROUP, src + u * u_step);
+                            cp_async_f32(dst + kTileRows * VBQ_GROUP + u * 2 * VBQ_GROUP, a.sigma + (src - a.mu) + u * u_step);
+                        }
                     }
                 }
             }
             cp_async_commit();
         };
-#pragma unroll
-        for (int k = 0; k < kStages - 1; ++k) stage_rows(row + k * U * RP, off + k * U * off_step, k);
+        int q0 = claim(), q1 = claim(), q2 = claim();   // tiles in flight (kStages - 1 = 3)
+        static_assert(kStages == 4, "the claim queue below holds kStages - 1 = 3 tiles");
+        stage(q0, 0);
+        stage(q1, 1);
+        stage(q2, 2);
         int slot = 0;
 
-        // one iteration: U coordinates of this thread (rows row, row+RP, ...); CHECK = row bounds must be tested
-        auto iteration = [&](auto check_tag) {
+        // one tile: U coordinates of this thread (tile rows par and 2 + par); CHECK = bounds must be tested
+        auto iteration = [&](auto check_tag, const int tile) {
             constexpr bool CHECK = decltype(check_tag)::value;
+            const int row = seg_row0 + tile * kTileRows + par;          // row of coordinate u = 0
+            const unsigned off = thr_off + (unsigned)tile * tile_step;
             float mu[U], sg[U];
             float2 nmu2[P], r2[P];   // r2 = sqrt(1/2)/sigma
+            bool ok[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const bool ok = !CHECK || row + u * RP < row_end;
-                mu[u] = ok ? myStage[slot * kSlotStride + u * kRowStride] : 0.0f;
-                float s = ok ? myStage[slot * kSlotStride + kArrStride + u * kRowStride] : 1.0f;
+                ok[u] = !CHECK || (c_ok && row + 2 * u < rows);
+                mu[u] = ok[u] ? myStage[slot * kTileFloats + u * 2 * VBQ_GROUP] : 0.0f;
+                float s = ok[u] ? myStage[slot * kTileFloats + kTileRows * VBQ_GROUP + u * 2 * VBQ_GROUP] : 1.0f;
                 if (logvar) s = sqrtf(expf(s));
                 sg[u] = s;
-            }
-            {   // refill the slot consumed in the previous iteration
-                const int ps = slot == 0 ? kStages - 1 : slot - 1;
-                stage_rows(row + (kStages - 1) * U * RP, off + (kStages - 1) * U * off_step, ps);
-                slot = slot == kStages - 1 ? 0 : slot + 1;
             }
 #pragma unroll
             for (int k = 0; k < P; ++k) {
@@ -336,8 +355,8 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
             for (int u = 0; u < U; ++u) {
                 const int n = wn[u], Pn = wP[u];
                 dist[u] = 0.0f;
-                if (!CHECK || row + u * RP < row_end) {
-                    const unsigned o = off + u * off_step;
+                if (ok[u]) {
+                    const unsigned o = off + u * u_step;
                     // sorted index q = (2i+1) 2^(N-n) - 1 with i = Pn - 2^n:  (2 Pn + 1) 2^(N-n) - 2^(N+1) - 1
                     const int q = ((2 * Pn + 1) << (N - n)) - (2 << N) - 1;
                     if (outm & 2u) qidx_c[o] = q;
@@ -355,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
                     }
                 }
             }
-            if (TOTALS) {   // the float32 terms of one iteration are added in float32, then accumulated in float64
+            if (TOTALS) {   // the float32 terms of one tile are added in float32, then accumulated in float64
                 float dsum = dist[0];
 #pragma unroll
                 for (int u = 1; u < U; ++u) dsum += dist[u];
@@ -363,90 +382,87 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
             }
         };
 
-        for (; row - rsub < p1 * RP; row += U * RP, off += U * off_step) {
-            cp_async_wait<kStages - 2>();        // this iteration's rows have landed
-            if (VEC) __syncwarp();               // ... for every lane of the warp (the tile is staged cooperatively)
-            if (row - rsub + U * RP <= full_rows) iteration(std::false_type{});
-            else iteration(std::true_type{});
+        while (q0 < n_tiles) {
+            const int nxt = claim();             // used at the end of the iteration: the atomic's latency is hidden
+            cp_async_wait<kStages - 2>();        // tile q0 has landed ...
+            __syncwarp();                        // ... for every lane of the warp (the tile is staged cooperatively)
+            if (q0 < full_tiles) iteration(std::false_type{}, q0);
+            else iteration(std::true_type{}, q0);
+            __syncwarp();                        // all lanes have read slot `slot`; (slot + 3) % 4 was read one tile ago
+            stage(nxt, slot == 0 ? kStages - 1 : slot - 1);
+            slot = slot == kStages - 1 ? 0 : slot + 1;
+            q0 = q1;
+            q1 = q2;
+            q2 = nxt;
         }
         cp_async_wait<0>();
     }
 
+#ifdef VBQ_TRACE
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t1));
+    __syncthreads();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tr_t2));
+    if (TOTALS && (threadIdx.x & 31) == 0) {   // per warp: start, own end, CTA end, segments, SM id
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        double *tr = a.partials + (size_t)kMaxGrid * VBQ_TOTALS * a.n_lambda + ((size_t)blockIdx.x * 32 + (threadIdx.x >> 5)) * 5;
+        tr[0] = (double)tr_t0; tr[1] = (double)tr_t1; tr[2] = (double)tr_t2; tr[3] = tr_segs + 1e-9 * (double)(clock64() - tr_c0); tr[4] = smid;
+    }
+#endif
     if (TOTALS) {
         // raw-length mode: the code length of depth n is n itself; no entropy model on this path
         double v[VBQ_TOTALS] = {(double)acc_level, (double)acc_level, 0.0, acc_dist};
-#pragma unroll
-        for (int k = 0; k < VBQ_TOTALS; ++k) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-            if ((threadIdx.x & 31) == 0) sRed[k][threadIdx.x >> 5] = v[k];
-        }
-        __syncthreads();
-        double *part = a.partials + ((size_t)lam * kMaxGrid + blockIdx.x) * VBQ_TOTALS;
-        if (threadIdx.x < VBQ_TOTALS) {
-            double s = 0.0;
-            for (int w = 0; w < kThreads / 32; ++w) s += sRed[threadIdx.x][w];
-            part[threadIdx.x] = s;
-            __threadfence();
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned t = atomicAdd(a.ticket + lam, 1u);
-            sLast = (t == gridDim.x - 1);
-        }
-        __syncthreads();
-        if (sLast && threadIdx.x < VBQ_TOTALS) {   // the last CTA of this lambda adds the partials in a fixed order
-            __threadfence();
-            const volatile double *p = a.partials + (size_t)lam * kMaxGrid * VBQ_TOTALS;
-            double s = a.accumulate ? a.totals[lam * VBQ_TOTALS + threadIdx.x] : 0.0;
-            for (unsigned b = 0; b < gridDim.x; ++b) s += p[b * VBQ_TOTALS + threadIdx.x];
-            a.totals[lam * VBQ_TOTALS + threadIdx.x] = s;
-            if (threadIdx.x == 0) a.ticket[lam] = 0u;
-        }
+        finish_totals<kThreads>(a, lam, v, sRed, &sLast);
     }
 }
 
-template <bool PRUNE, bool TOTALS, int NT, int OUT, bool VEC, int U, int T>
+template <bool PRUNE, bool TOTALS, int NT, int OUT, bool VEC, int T>
 static int launch_bisect(QArgs a, int dev, int sms, cudaStream_t st) {
-    constexpr int rows_per_pass = T / VBQ_GROUP;
-    a.passes = (a.rows + rows_per_pass - 1) / rows_per_pass;
+    a.passes = (a.rows + kTileRows - 1) / kTileRows;   // tiles per group
     a.total_units = a.passes * a.n_groups;
-    long long gx = (a.total_units + U - 1) / U;
+    long long gx = (a.total_units + (T / 32) - 1) / (T / 32);   // at least one tile per warp
     if (gx > sms) gx = sms;
     if (gx > kMaxGrid) gx = kMaxGrid;
+    if (gx < 1) gx = 1;
     const size_t smem = ((size_t)kPadEntries * VBQ_GROUP + (size_t)(kSmemDepth + 1) * VBQ_GROUP +
-                         (size_t)kStages * 2 * U * T) * sizeof(float);   // the same ring size with and without VEC
-    auto kern = vbq_bisect_kernel<PRUNE, TOTALS, NT, OUT, VEC, U, T>;
+                         (size_t)(T / 32) * kStages * kTileFloats) * sizeof(float);
+    auto kern = vbq_bisect_kernel<PRUNE, TOTALS, NT, OUT, VEC, T>;
     VBQ_ENSURE_MAX_SMEM(kern, dev);
     kern<<<dim3((int)gx, a.n_lambda), T, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return VBQ_OK;
 }
 
-template <bool PRUNE, bool TOTALS, int NT, int U, int T>
+template <bool PRUNE, bool TOTALS, int NT, int T>
 static int launch_bisect3(const QArgs &a, int dev, int sms, cudaStream_t st) {
     // the two output sets the facade and the benchmark ask for are compiled in; anything else tests the mask at run time
-    const bool vec = U == 2 && a.C % 4 == 0 && (((uintptr_t)a.mu | (uintptr_t)a.sigma) & 15) == 0;
-    if (!vec) return launch_bisect<PRUNE, TOTALS, NT, -1, false, U, T>(a, dev, sms, st);
+    const bool vec = a.C % 4 == 0 && (((uintptr_t)a.mu | (uintptr_t)a.sigma) & 15) == 0;
+    if (!vec) return launch_bisect<PRUNE, TOTALS, NT, -1, false, T>(a, dev, sms, st);
     switch (a.outm & 15u) {
-        case 2u | 8u: return launch_bisect<PRUNE, TOTALS, NT, 2 | 8, true, U, T>(a, dev, sms, st);   // sorted index + code length
-        case 1u | 4u: return launch_bisect<PRUNE, TOTALS, NT, 1 | 4, true, U, T>(a, dev, sms, st);   // z_hat + depth
-        default: return launch_bisect<PRUNE, TOTALS, NT, -1, true, U, T>(a, dev, sms, st);
+        case 2u | 8u: return launch_bisect<PRUNE, TOTALS, NT, 2 | 8, true, T>(a, dev, sms, st);   // sorted index + code length
+        case 1u | 4u: return launch_bisect<PRUNE, TOTALS, NT, 1 | 4, true, T>(a, dev, sms, st);   // z_hat + depth
+        default: return launch_bisect<PRUNE, TOTALS, NT, -1, true, T>(a, dev, sms, st);
     }
 }
 
-template <bool PRUNE, int U, int T>
+template <bool PRUNE, int T>
 static int launch_bisect2(const QArgs &a, int dev, int sms, cudaStream_t st) {
     const bool tot = a.totals != nullptr;
     if (a.N == kSmemDepth)
-        return tot ? launch_bisect3<PRUNE, true, kSmemDepth, U, T>(a, dev, sms, st)
-                   : launch_bisect3<PRUNE, false, kSmemDepth, U, T>(a, dev, sms, st);
-    return tot ? launch_bisect3<PRUNE, true, 0, U, T>(a, dev, sms, st) : launch_bisect3<PRUNE, false, 0, U, T>(a, dev, sms, st);
+        return tot ? launch_bisect3<PRUNE, true, kSmemDepth, T>(a, dev, sms, st)
+                   : launch_bisect3<PRUNE, false, kSmemDepth, T>(a, dev, sms, st);
+    return tot ? launch_bisect3<PRUNE, true, 0, T>(a, dev, sms, st) : launch_bisect3<PRUNE, false, 0, T>(a, dev, sms, st);
 }
 
 // raw code lengths (no length table, no entropy model), max_bits_per_coord <= 10; returns -1 if not applicable
 int vbq_launch_quantize_bisect(const QArgs &a, int dev, int sms, cudaStream_t st) {
     if (a.len || a.em || a.N > kSmemDepth) return -1;
     const bool prune = !(a.flags & VBQ_FLAG_NO_PRUNE);
-    return prune ? launch_bisect2<true, 2, 640>(a, dev, sms, st) : launch_bisect2<false, 2, 640>(a, dev, sms, st);
+    static const int tune = getenv("VBQ_TUNE") ? atoi(getenv("VBQ_TUNE")) : 0;   // development: threads / 128
+    if (!prune) {
+        if (tune == 4) return launch_bisect2<false, 512>(a, dev, sms, st);
+        if (tune == 5) return launch_bisect2<false, 640>(a, dev, sms, st);
+        if (tune == 7) return launch_bisect2<false, 896>(a, dev, sms, st);
+    }
+    return prune ? launch_bisect2<true, 768>(a, dev, sms, st) : launch_bisect2<false, 768>(a, dev, sms, st);
 }

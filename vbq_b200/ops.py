@@ -25,6 +25,7 @@ FLAG_NO_SWEEP = _lib.FLAG_NO_SWEEP
 FLAG_REFERENCE_WALK = _lib.FLAG_REFERENCE_WALK
 FLAG_RESERVE_SM = _lib.FLAG_RESERVE_SM
 FLAG_BRACKET_WALK = _lib.FLAG_BRACKET_WALK
+FLAG_WORKSPACE_ZEROED = _lib.FLAG_WORKSPACE_ZEROED
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -114,8 +115,42 @@ def quantize_into(mu, sigma, table, packed, penalty, length, entropy_model, max_
 
 
 def quantize_workspace(n_lambda, device):
+    """Zero-filled totals workspace.  Calls leave its ticket counters zero again, so a workspace from this function
+    may always be passed together with FLAG_WORKSPACE_ZEROED (quantize_into does so when `workspace_zeroed`)."""
     n = _lib.load().vbq_quantize_workspace_bytes(n_lambda)
-    return torch.empty((n + 7) // 8, dtype=torch.float64, device=device)
+    return torch.zeros((n + 7) // 8, dtype=torch.float64, device=device)
+
+
+class QuantizePlan:
+    """A vbq_quantize call with caller-owned, fixed buffers, captured once into a CUDA graph: `run()` is a single
+    cudaGraphLaunch on the current stream (the Python + ctypes + launch path costs more host time than the kernel
+    runs for a Kodak-sized batch).  `graph=False` keeps the eager call (same results)."""
+
+    def __init__(self, mu, sigma, table, packed, penalty, length, entropy_model, max_bits, zhat=None, qidx=None,
+                 level=None, bits=None, em_bits=None, totals=None, flags=0, graph=True):
+        self.totals = totals
+        ws = quantize_workspace(penalty.shape[0], mu.device) if totals is not None else None
+        self._args = (mu, sigma, table, packed, penalty, length, entropy_model, max_bits)
+        self._kw = dict(zhat=zhat, qidx=qidx, level=level, bits=bits, em_bits=em_bits, totals=totals, workspace=ws,
+                        flags=flags | (FLAG_WORKSPACE_ZEROED if ws is not None else 0))
+        self._graph = None
+        if graph:
+            self._call()                       # sets the kernels' shared-memory attributes outside the capture
+            torch.cuda.synchronize(mu.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._call()
+            self._graph = g
+
+    def _call(self):
+        quantize_into(*self._args, **self._kw)
+
+    def run(self):
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._call()
+        return self.totals
 
 
 # ------------------------------------------------------------------------------------------------------
