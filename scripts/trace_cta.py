@@ -19,7 +19,7 @@ for it in range(NIT):
     if it == NIT - 2: evs[0].record()
     if it == NIT - 1: evs[1].record()
     ops.quantize_into(mu, sigma, q.all_code_points, q._packed, pen, length, None, bench.N_BITS, qidx=qidx, bits=bits,
-                      totals=tot, workspace=ws, flags=2)
+                      totals=tot, workspace=ws, flags=2 | 256)
 evs[2].record()
 torch.cuda.synchronize()
 print("NIT", NIT, "event time of the last two launches us: %.2f %.2f" % (1e3 * evs[0].elapsed_time(evs[1]), 1e3 * evs[1].elapsed_time(evs[2])))

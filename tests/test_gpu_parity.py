@@ -346,3 +346,34 @@ def test_bisection_rejects_non_monotone_penalties():
         res.append((z, lv))
     for z, lv in res[1:]:
         assert torch.equal(z, res[0][0]) and torch.equal(lv, res[0][1])
+
+
+@pytest.mark.parametrize("N,C,rows,n_lambda", [(10, 48, 9000, 16), (10, 21, 1001, 130), (7, 16, 640, 5), (0, 3, 50, 2)])
+def test_bisection_sweep_equals_bracket_walk_sweep(N, C, rows, n_lambda):
+    """All lambdas from one certified-bisection walk (vbq_bisect_sweep_kernel, the default for raw code lengths) vs the
+    round-1 sweep kernel (VBQ_FLAG_BRACKET_WALK: both bracket ends, IEEE scores, two running maxima) and vs one walk
+    per lambda: identical outputs incl. lambda = 0, the chunking beyond 100 lambdas, ragged C; totals within 1e-6."""
+    import vbq_b200
+    from vbq_b200 import ops
+    pr = H.make_prior(C, seed=50 + N)
+    q = vbq_b200.ChannelwisePriorCDFQuantizer(C, N)
+    q.set_code_points(ops.build_code_points_learned(_dev(pr.packed()), N))
+    table = q.all_code_points.cpu().numpy()
+    mu, sigma, _ = H.make_latents(pr, rows, 77, table=table)
+    srt = q.code_points_by_channel.cpu().numpy()
+    rng = np.random.default_rng(3)
+    idx = rng.integers(0, srt.shape[1], (rows, C))
+    on = srt[np.arange(C)[None, :], idx]
+    mu = np.where(rng.integers(0, 5, (rows, C)) == 0, on, mu).astype(np.float32)   # exact hits: ties at lambda = 0
+    lambs = [0.0] + [float(l) for l in 2 ** np.linspace(-8, 7, n_lambda - 1)]
+    outs = ops.OUT_ZHAT | ops.OUT_QIDX | ops.OUT_LEVEL | ops.OUT_BITS | ops.OUT_TOTALS
+    a = q.quantize(_dev(mu), _dev(sigma), lambs, outputs=outs)
+    b = q.quantize(_dev(mu), _dev(sigma), lambs, outputs=outs, flags=ops.FLAG_BRACKET_WALK)
+    c = q.quantize(_dev(mu), _dev(sigma), lambs, outputs=outs, flags=ops.FLAG_NO_SWEEP | ops.FLAG_REFERENCE_WALK)
+    for k in ("zhat", "qidx", "level", "bits"):
+        assert torch.equal(a[k], b[k]), k
+        assert torch.equal(a[k], c[k]), k
+    assert torch.equal(a["totals"][:, :3], b["totals"][:, :3])
+    assert torch.allclose(a["totals"][:, 3], b["totals"][:, 3], rtol=1e-6, atol=1e-9)
+    t = q.quantize(_dev(mu), _dev(sigma), lambs, outputs=ops.OUT_TOTALS)["totals"]     # totals-only path
+    assert torch.allclose(t, a["totals"], rtol=1e-12, atol=0)

@@ -162,7 +162,8 @@ extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long r
         b.accumulate = r0 > 0 || (flags & VBQ_FLAG_ACCUMULATE_TOTALS);
         int st_;
         if (!(flags & VBQ_FLAG_NO_SWEEP)) {   // several lambdas: one walk per coordinate serves all of them
-            st_ = vbq_launch_sweep(b, dev, sms, st);
+            st_ = vbq_launch_sweep_bisect(b, dev, sms, st);
+            if (st_ < 0) st_ = vbq_launch_sweep(b, dev, sms, st);
             if (st_ >= 0) {
                 RETURN_IF(st_);
                 continue;

@@ -28,68 +28,7 @@
 // non-negative, the coordinate is redone by `reference_search`, the literal two-ended walk with IEEE arithmetic.
 #include <stdlib.h>
 
-#include <type_traits>
-
-#include "tree.cuh"
-
-constexpr unsigned kKeyGuard = 192u;
-constexpr unsigned kKeyMask = 0xfffffff0u;
-
-// Literal restatement of the reference search for one coordinate (slow path): both bracket ends of every depth,
-// IEEE float32 scores, first maximum in the order left_0..left_N, right_1..right_N.  Returns depth << 16 | index.
-// sTc = this channel's column of the padded shared-memory tree, sPenc = its penalties (stride VBQ_GROUP).
-static __device__ __noinline__ int reference_search(const float *sTc, const float *sPenc, float mu, float sg, int N) {
-    const float rs = rcp_rn(sg);
-    const float z0 = sTc[entry_of(0, 0) * VBQ_GROUP];
-    float bestL = score_exact(z0, mu, sg, rs, -sPenc[0]), bestR = -CUDART_INF_F;
-    int nL = 0, iL = 0, nR = 0, iR = 0;
-    int ip = mu > z0 ? 1 : 0;   // index of the path node at the next depth
-    for (int n = 1; n <= N; ++n) {
-        const float zp = sTc[entry_of(n, ip) * VBQ_GROUP];
-        const int b = mu > zp ? 1 : 0;
-        const int fg = ip + b;   // number of depth-n points below mu = searchsorted(side='left'), quantizer.py:74
-        const int il = clamp_index(fg, n, N, false), ir = clamp_index(fg, n, N, true);
-        const float npn = -sPenc[n * VBQ_GROUP];
-        const float sl = score_exact(sTc[entry_of(n, il) * VBQ_GROUP], mu, sg, rs, npn);
-        const float sr = score_exact(sTc[entry_of(n, ir) * VBQ_GROUP], mu, sg, rs, npn);
-        if (sl > bestL) { bestL = sl; nL = n; iL = il; }
-        if (sr > bestR) { bestR = sr; nR = n; iR = ir; }
-        ip = 2 * ip + b;
-    }
-    return bestR > bestL ? (nR << 16 | iR) : (nL << 16 | iL);
-}
-
-__device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, relative error <= 2^-23
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
-// (bits & mask) | n as ONE LOP3: the mask 0xfffffff0 sits in a register, the depth is an immediate
-template <int DEPTH>
-__device__ __forceinline__ unsigned make_key(float loss, unsigned mask) {
-    unsigned k;
-    asm("lop3.b32 %0, %1, %2, %3, 0xEC;" : "=r"(k) : "r"(__float_as_uint(loss)), "n"(DEPTH), "r"(mask));
-    return k;
-}
-
-// Work decomposition.  A TILE is 4 consecutive rows x the 16 channels of one group: one warp iteration (lane =
-// (row parity, channel), two coordinates per thread: rows 2u + parity, u = 0, 1).  The tiles of a launch, ordered by
-// (group, row), are cut into one contiguous span per CTA; inside a span the warps of the CTA CLAIM tiles from a
-// shared-memory counter, kStages-1 tiles ahead of the one they compute (claim -> cp.async -> compute), so that all
-// warps of a CTA finish within one tile of each other whatever the scheduler's warp priorities were.  A CTA whose
-// span crosses a group boundary loads a second tree; the cut positions charge kSwitchTiles tiles for that.
-constexpr int kTileRows = 4;
-constexpr int kTileFloats = 2 * kTileRows * VBQ_GROUP;   // mu rows then sigma rows: [2][4][16]
-constexpr int kSwitchTiles = 32;
-
-// first real tile (in group-major order) of virtual position v: every group is preceded by kSwitchTiles virtual tiles
-__device__ __forceinline__ long long span_cut(long long v, long long tiles_per_group, int n_groups) {
-    const long long vg = tiles_per_group + kSwitchTiles;
-    const long long g = min(v / vg, (long long)n_groups);
-    const long long o = v - g * vg;
-    return g * tiles_per_group + max(0ll, o - kSwitchTiles);
-}
+#include "bisect.cuh"
 
 // NT > 0: max_bits_per_coord == NT at compile time; NT == 0: runtime depth (<= kSmemDepth).
 // OUT >= 0: the set of requested outputs (bit 0 zhat, 1 qidx, 2 level, 3 bits) is known at compile time; OUT < 0: runtime.
@@ -150,29 +89,9 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
         const int n_tiles = (int)min(tpg - t0, u1 - unit);   // tiles t0 .. t0 + n_tiles - 1 of group g
         unit += n_tiles;
 
+        __syncthreads();                     // every warp has left the previous segment
+        if (threadIdx.x == 0) sNext = 0;
         __syncthreads();
-        {
-            const float4 *src = reinterpret_cast<const float4 *>(a.packed + (size_t)g * kPadEntries * VBQ_GROUP);
-            float4 *dst = reinterpret_cast<float4 *>(sT);
-            for (int k = threadIdx.x; k < kPadEntries * (VBQ_GROUP / 4); k += kThreads) dst[k] = __ldg(src + k);
-            if (threadIdx.x < VBQ_GROUP) {
-                const int j = threadIdx.x;
-                const int cj = min(g * VBQ_GROUP + j, C - 1);
-                const size_t po = ((size_t)lam * a.pen_channels + (a.pen_channels == 1 ? 0 : cj)) * (N + 1);
-                float prev = 0.0f;
-                bool mono = true;   // certified ranking needs 0 <= pen_0 <= pen_1 <= ... (false for NaN)
-                for (int n = 0; n <= kSmemDepth; ++n) {
-                    const float p = n <= N ? a.pen[po + n] : CUDART_INF_F;
-                    mono = mono && (p >= prev);
-                    prev = p;
-                    sPen[n * VBQ_GROUP + j] = p;
-                }
-                sGuard[j] = mono ? kKeyGuard : 0xffffffffu;   // 0xffffffff: every coordinate takes the slow path
-            }
-            if (threadIdx.x == 0) sNext = 0;
-        }
-        __syncthreads();
-
         const int c = g * VBQ_GROUP + col;
         const bool c_ok = c < C;
         const int cc = min(c, C - 1);
@@ -184,11 +103,6 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
         int *qidx_c = a.qidx ? a.qidx + lam_off : nullptr;
         int *level_c = a.level ? a.level + lam_off : nullptr;
         float *bits_c = a.bits ? a.bits + lam_off : nullptr;
-        float pen[kSmemDepth + 1];
-#pragma unroll
-        for (int n = 0; n <= kSmemDepth; ++n) pen[n] = sPen[n * VBQ_GROUP + col];
-        const unsigned guard = sGuard[col];
-        const float z0 = sTc[entry_of(0, 0) * VBQ_GROUP];
         // tiles below full_tiles have all 4 rows inside the matrix; a group with 16 real channels needs no predicates
         const bool group_full = g * VBQ_GROUP + VBQ_GROUP <= C;
         const int full_tiles = group_full ? min(n_tiles, (rows - seg_row0) / kTileRows) : 0;
@@ -229,6 +143,33 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
         stage(q1, 1);
         stage(q2, 2);
         int slot = 0;
+
+        // the group's tree and penalties, while the first tiles are in flight
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(a.packed + (size_t)g * kPadEntries * VBQ_GROUP);
+            float4 *dst = reinterpret_cast<float4 *>(sT);
+            for (int k = threadIdx.x; k < kPadEntries * (VBQ_GROUP / 4); k += kThreads) dst[k] = __ldg(src + k);
+            if (threadIdx.x < VBQ_GROUP) {
+                const int j = threadIdx.x;
+                const int cj = min(g * VBQ_GROUP + j, C - 1);
+                const size_t po = ((size_t)lam * a.pen_channels + (a.pen_channels == 1 ? 0 : cj)) * (N + 1);
+                float prev = 0.0f;
+                bool mono = true;   // certified ranking needs 0 <= pen_0 <= pen_1 <= ... (false for NaN)
+                for (int n = 0; n <= kSmemDepth; ++n) {
+                    const float p = n <= N ? a.pen[po + n] : CUDART_INF_F;
+                    mono = mono && (p >= prev);
+                    prev = p;
+                    sPen[n * VBQ_GROUP + j] = p;
+                }
+                sGuard[j] = mono ? kKeyGuard : 0xffffffffu;   // 0xffffffff: every coordinate takes the slow path
+            }
+        }
+        __syncthreads();
+        float pen[kSmemDepth + 1];
+#pragma unroll
+        for (int n = 0; n <= kSmemDepth; ++n) pen[n] = sPen[n * VBQ_GROUP + col];
+        const unsigned guard = sGuard[col];
+        const float z0 = sTc[entry_of(0, 0) * VBQ_GROUP];
 
         // one tile: U coordinates of this thread (tile rows par and 2 + par); CHECK = bounds must be tested
         auto iteration = [&](auto check_tag, const int tile) {
@@ -345,7 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
             if (gapmin <= guard) {   // some coordinate is not certified (or penalties not monotone): literal search
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int r = reference_search(sTc, sPen + col, mu[u], sg[u], N);
+                    const int r = reference_search(sTc, sPen + col, VBQ_GROUP, mu[u], sg[u], N);
                     wn[u] = r >> 16;
                     wP[u] = (1 << wn[u]) + (r & 0xffff);
                 }
