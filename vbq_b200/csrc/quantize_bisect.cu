@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
 
     double acc_dist = 0.0;
     int acc_level = 0;   // < 2^31: at most 2^29 coordinates per launch, depth <= 10
+    pdl_wait();   // launched with programmatic stream serialization: nothing global is touched before this point
 #ifdef VBQ_TRACE
     unsigned long long tr_t0 = 0, tr_t1 = 0, tr_t2 = 0;
     int tr_segs = 0;
@@ -369,8 +370,7 @@ static int launch_bisect(QArgs a, int dev, int sms, cudaStream_t st) {
                          (size_t)(T / 32) * kStages * kTileFloats) * sizeof(float);
     auto kern = vbq_bisect_kernel<PRUNE, TOTALS, NT, OUT, VEC, T>;
     VBQ_ENSURE_MAX_SMEM(kern, dev);
-    kern<<<dim3((int)gx, a.n_lambda), T, smem, st>>>(a);
-    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(launch_pdl(kern, dim3((int)gx, a.n_lambda), T, smem, st, a));
     return VBQ_OK;
 }
 

@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_sweep_kernel(const QAr
     if (TOTALS) {
         for (int k = threadIdx.x; k < kWarps * L * 2; k += kThreads) sAcc[k] = 0.0;
     }
+    pdl_wait();   // launched with programmatic stream serialization: nothing global is touched before this point
     // penalties are the same for every group (pen_channels == 1): staged once
     for (int lam = threadIdx.x; lam < L; lam += kThreads) {
         float prev = 0.0f;
@@ -329,8 +330,7 @@ static int launch_bisect_sweep(QArgs a, int dev, int sms, cudaStream_t st) {
         // stay 8-byte aligned: kPenSlots * 4 = 48 bytes per lambda is already a multiple of 16
         const size_t smem = fixed + per_lambda * b.n_lambda;
         VBQ_ENSURE_MAX_SMEM(kern, dev);
-        kern<<<dim3((int)gx, 1), T, smem, st>>>(b);
-        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(launch_pdl(kern, dim3((int)gx, 1), T, smem, st, b));
     }
     return VBQ_OK;
 }
