@@ -1,3 +1,4 @@
 python -m pytest tests -m gpu -q -x 2>&1 | tail -3
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-bash scripts/profile_round.sh 2>&1 | tail -6
+python scripts/bench_configs.py emb sweep 2>&1 | cut -c1-200
+python bench.py --steps 200 --no-cpu | cut -c1-120
+python bench.py --steps 200 --no-cpu | cut -c1-120

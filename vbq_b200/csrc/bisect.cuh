@@ -34,6 +34,16 @@ static __device__ __noinline__ int reference_search(const float *sTc, const floa
     return bestR > bestL ? (nR << 16 | iR) : (nL << 16 | iL);
 }
 
+// Next unclaimed tile of the CTA's current segment: lane 0 increments the shared counter, the warp gets the old value.
+// atom.inc (wrap bound 2^31-1, i.e. a plain increment) on purpose: for atomicAdd / atom.add ptxas emits its
+// warp-aggregation sequence (vote, find-leader, popc, lanemask: 17 instructions) around this single-lane atomic.
+__device__ __forceinline__ int claim_tile(int *counter, int lane) {
+    int j = 0;
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(counter);
+    if (lane == 0) asm volatile("atom.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(j) : "r"(addr) : "memory");
+    return __shfl_sync(0xffffffffu, j, 0);
+}
+
 __device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, relative error <= 2^-23
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

@@ -115,11 +115,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
         float *prod_dst = VEC ? wStage + (lane >> 4) * (kTileRows * VBQ_GROUP) + prod_row * VBQ_GROUP + (lane & 3) * 4
                               : wStage + par * VBQ_GROUP + col;
         const bool prod_col_ok = VEC ? prod_col < C : c_ok;
-        auto claim = [&]() -> int {
-            int j = 0;
-            if (lane == 0) j = atomicAdd(&sNext, 1);
-            return __shfl_sync(0xffffffffu, j, 0);
-        };
+        auto claim = [&]() -> int { return claim_tile(&sNext, lane); };
         auto stage = [&](int j, int slot) {   // every call commits exactly one group (possibly empty)
             if (j < n_tiles) {
                 const float *src = prod_src + (size_t)j * tile_step;
@@ -236,24 +232,26 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
                 }
                 m_done = n;
             };
-            auto prune_here = [&](int n) -> bool {
+            unsigned run_min[U];   // PRUNE: minimum of the keys of the depths scored so far, updated at every test
+#pragma unroll
+            for (int u = 0; u < U; ++u) run_min[u] = 0xffffffffu;
+            auto prune_here = [&](auto n_tag) -> bool {
+                constexpr int n = decltype(n_tag)::value;
                 // sound early exit: every deeper loss is >= pen_n, so once the best key plus the guard is below the
                 // key of pen_n no deeper candidate can win or come within the guard
                 const unsigned floor_key = __float_as_uint(pen[n]) & kKeyMask;
                 bool done = guard == kKeyGuard && floor_key > kKeyGuard + 16u;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    unsigned m = key[u][0];
-#pragma unroll
-                    for (int j = 1; j <= kSmemDepth; ++j)
-                        if (j < n) m = min(m, key[u][j]);
-                    done = done && m < floor_key - (kKeyGuard + 16u);
+                    run_min[u] = __vimin3_u32(run_min[u], key[u][n - 3], key[u][n - 2]);
+                    run_min[u] = min(run_min[u], key[u][n - 1]);
+                    done = done && run_min[u] < floor_key - (kKeyGuard + 16u);
                 }
                 return __all_sync(0xffffffffu, done);
             };
 #define VBQ_DEPTH(n_)                                                        \
     if ((NT > 0 ? n_ <= NT : n_ <= N) && !stop) {                            \
-        if (PRUNE && n_ % 3 == 0 && prune_here(n_)) stop = true;             \
+        if (PRUNE && n_ % 3 == 0 && prune_here(std::integral_constant<int, n_>{})) stop = true; \
         else depth(std::integral_constant<int, n_>{});                       \
     }
             bool stop = false;
@@ -382,6 +380,7 @@ static int launch_bisect3(const QArgs &a, int dev, int sms, cudaStream_t st) {
     switch (a.outm & 15u) {
         case 2u | 8u: return launch_bisect<PRUNE, TOTALS, NT, 2 | 8, true, T>(a, dev, sms, st);   // sorted index + code length
         case 1u | 4u: return launch_bisect<PRUNE, TOTALS, NT, 1 | 4, true, T>(a, dev, sms, st);   // z_hat + depth
+        case 1u: return launch_bisect<PRUNE, TOTALS, NT, 1, true, T>(a, dev, sms, st);            // z_hat (word embeddings)
         default: return launch_bisect<PRUNE, TOTALS, NT, -1, true, T>(a, dev, sms, st);
     }
 }
@@ -399,11 +398,6 @@ static int launch_bisect2(const QArgs &a, int dev, int sms, cudaStream_t st) {
 int vbq_launch_quantize_bisect(const QArgs &a, int dev, int sms, cudaStream_t st) {
     if (a.len || a.em || a.N > kSmemDepth) return -1;
     const bool prune = !(a.flags & VBQ_FLAG_NO_PRUNE);
-    static const int tune = getenv("VBQ_TUNE") ? atoi(getenv("VBQ_TUNE")) : 0;   // development: threads / 128
-    if (!prune) {
-        if (tune == 4) return launch_bisect2<false, 512>(a, dev, sms, st);
-        if (tune == 5) return launch_bisect2<false, 640>(a, dev, sms, st);
-        if (tune == 7) return launch_bisect2<false, 896>(a, dev, sms, st);
-    }
+    // 768 threads (24 warps, 80 registers): measured best of 512 / 640 / 768 / 896
     return prune ? launch_bisect2<true, 768>(a, dev, sms, st) : launch_bisect2<false, 768>(a, dev, sms, st);
 }

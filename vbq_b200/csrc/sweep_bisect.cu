@@ -89,11 +89,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_sweep_kernel(const QAr
         float *prod_dst = VEC ? wStage + (lane >> 4) * (kTileRows * VBQ_GROUP) + prod_row * VBQ_GROUP + (lane & 3) * 4
                               : wStage + par * VBQ_GROUP + col;
         const bool prod_col_ok = VEC ? prod_col < C : c_ok;
-        auto claim = [&]() -> int {
-            int j = 0;
-            if (lane == 0) j = atomicAdd(&sNext, 1);
-            return __shfl_sync(0xffffffffu, j, 0);
-        };
+        auto claim = [&]() -> int { return claim_tile(&sNext, lane); };
         auto stage = [&](int j, int slot) {   // every call commits exactly one group (possibly empty)
             if (j < n_tiles) {
                 const float *src = prod_src + (size_t)j * tile_step;

@@ -63,7 +63,11 @@ class GaussianCodebook:
         per_level = self._level_lengths(self.lengths if bitlengths is None else bitlengths).astype(np.float32)
         pen = np.stack([np.float32(b) * per_level for b in betas])[:, None, :]
         pen = torch.from_numpy(np.ascontiguousarray(pen, dtype=np.float32)).to(self.device)
-        length = torch.from_numpy(np.broadcast_to(per_level, (len(betas), 1, N + 1)).copy()).to(self.device)
+        # the notebook's default lengths are the bit depths themselves: no length table, which lets vbq_quantize use
+        # the certified-bisection kernels (raw code lengths); custom bitlengths go through the length-table path
+        length = None
+        if bitlengths is not None and not np.array_equal(per_level, np.arange(N + 1, dtype=np.float32)):
+            length = torch.from_numpy(np.broadcast_to(per_level, (len(betas), 1, N + 1)).copy()).to(self.device)
         m = means.reshape(-1)
         s = stds.reshape(-1)
         n = m.numel()
