@@ -15,7 +15,9 @@
 
 constexpr int kPenSlots = 12;   // per lambda: penalties of depths 0..10 and the guard word, 48 bytes (three float4)
 
-template <bool TOTALS, bool VEC, int kThreads>
+// OUTS: per-coordinate outputs are requested (otherwise the call returns only the per-lambda totals and the lambda loop
+// carries no output pointers, masks or addresses)
+template <bool TOTALS, bool OUTS, bool VEC, int kThreads>
 __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_sweep_kernel(const QArgs a) {
     constexpr int U = 2;
     constexpr int kWarps = kThreads / 32;
@@ -44,7 +46,6 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_sweep_kernel(const QAr
     const unsigned kmask = a.keymask;
     float *wStage = sStage + warp * (kStages * kTileFloats);
     const float *myStage = wStage + par * VBQ_GROUP + col;
-    const bool any_out = a.zhat || a.qidx || a.level || a.bits;
     double *wAcc = sAcc + (size_t)warp * L * 2;
 
     if (TOTALS) {
@@ -173,7 +174,12 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_sweep_kernel(const QAr
             const int kd = N + 1;   // depth of the node K points at
 
             // ---- every lambda from the registers ----------------------------------------------------------------
-            for (int lam = 0; lam < L; ++lam) {
+            // lane j of the warp keeps the tile's sums of lambda lb + j; they reach shared memory once per 32 lambdas
+            for (int lb = 0; lb < L; lb += 32) {
+            int my_level = 0;
+            float my_dist = 0.0f;
+            const int lend = min(L, lb + 32);
+            for (int lam = lb; lam < lend; ++lam) {
                 const float4 *pl = reinterpret_cast<const float4 *>(sPenL + lam * kPenSlots);
                 const float4 pa = pl[0], pb = pl[1], pc = pl[2];
                 const float pen[kSmemDepth + 1] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w, pc.x, pc.y, pc.z};
@@ -219,9 +225,9 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_sweep_kernel(const QAr
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int n = wn[u], Pn = wP[u];
-                    if (ok[u] && (TOTALS || any_out)) {
+                    if ((TOTALS || OUTS) && ok[u]) {
                         const float zh = lds_pure((unsigned)(imad(n, 2 * kRowStrideBytes, imad(Pn, kRowStrideBytes, pbi))));
-                        if (any_out) {
+                        if (OUTS) {
                             const size_t o = lam_off + off + u * u_step;
                             const int q = ((2 * Pn + 1) << (N - n)) - (2 << N) - 1;
                             if (a.zhat) a.zhat[o] = zh;
@@ -240,11 +246,16 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_sweep_kernel(const QAr
                     t_level = __reduce_add_sync(0xffffffffu, t_level);
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) t_dist += __shfl_xor_sync(0xffffffffu, t_dist, o);
-                    if (lane == 0) {
-                        wAcc[lam * 2 + 0] += (double)t_level;
-                        wAcc[lam * 2 + 1] += (double)t_dist;
+                    if (lane == lam - lb) {   // the butterfly left the sums in every lane
+                        my_level = t_level;
+                        my_dist = t_dist;
                     }
                 }
+            }
+            if (TOTALS && lb + lane < L) {
+                wAcc[(lb + lane) * 2 + 0] += (double)my_level;
+                wAcc[(lb + lane) * 2 + 1] += (double)my_dist;
+            }
             }
 
             __syncwarp();
@@ -294,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_sweep_kernel(const QAr
     }
 }
 
-template <bool TOTALS, bool VEC, int T>
+template <bool TOTALS, bool OUTS, bool VEC, int T>
 static int launch_bisect_sweep(QArgs a, int dev, int sms, cudaStream_t st) {
     a.passes = (a.rows + kTileRows - 1) / kTileRows;
     a.total_units = a.passes * a.n_groups;
@@ -307,7 +318,7 @@ static int launch_bisect_sweep(QArgs a, int dev, int sms, cudaStream_t st) {
     int max_l = (int)((220 * 1024 - fixed) / per_lambda);
     max_l &= ~3;   // keeps the accumulators behind the penalty block 16-byte aligned
     if (max_l < 4) return -1;
-    auto kern = vbq_bisect_sweep_kernel<TOTALS, VEC, T>;
+    auto kern = vbq_bisect_sweep_kernel<TOTALS, OUTS, VEC, T>;
     const int n_lambda = a.n_lambda;
     for (int l0 = 0; l0 < n_lambda; l0 += max_l) {   // lambdas beyond the shared-memory budget are served in chunks
         QArgs b = a;
@@ -338,6 +349,11 @@ int vbq_launch_sweep_bisect(const QArgs &a, int dev, int sms, cudaStream_t st) {
     const bool tot = a.totals != nullptr;
     const bool vec = a.C % 4 == 0 && (((uintptr_t)a.mu | (uintptr_t)a.sigma) & 15) == 0;
     constexpr int T = 768;
-    if (vec) return tot ? launch_bisect_sweep<true, true, T>(a, dev, sms, st) : launch_bisect_sweep<false, true, T>(a, dev, sms, st);
-    return tot ? launch_bisect_sweep<true, false, T>(a, dev, sms, st) : launch_bisect_sweep<false, false, T>(a, dev, sms, st);
+    const bool outs = a.zhat || a.qidx || a.level || a.bits;
+    if (!tot && !outs) return VBQ_OK;   // nothing requested
+    if (vec) {
+        if (!outs) return launch_bisect_sweep<true, false, true, T>(a, dev, sms, st);
+        return tot ? launch_bisect_sweep<true, true, true, T>(a, dev, sms, st) : launch_bisect_sweep<false, true, true, T>(a, dev, sms, st);
+    }
+    return tot ? launch_bisect_sweep<true, true, false, T>(a, dev, sms, st) : launch_bisect_sweep<false, true, false, T>(a, dev, sms, st);
 }
