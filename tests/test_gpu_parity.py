@@ -290,7 +290,8 @@ def test_garbage_inputs_stay_in_bounds(flags):
             assert np.array_equal(np.take_along_axis(srt.T, qi[i].astype(np.int64), axis=0), out["zhat"][i].cpu().numpy())
 
 
-@pytest.mark.parametrize("N,C,rows", [(10, 48, 20000), (10, 5, 777), (6, 17, 3000), (4, 33, 257), (1, 3, 40), (0, 2, 40)])
+@pytest.mark.parametrize("N,C,rows", [(10, 48, 20000), (10, 5, 777), (6, 17, 3000), (4, 33, 257), (1, 3, 40), (0, 2, 40),
+                                      (12, 20, 3000), (16, 16, 2000), (11, 7, 501)])
 def test_bisection_equals_reference_walk(N, C, rows):
     """The default single-lambda kernel (certified bisection: one path node per depth, approximate ranking with a
     guard band, literal search for uncertified coordinates) vs VBQ_FLAG_REFERENCE_WALK and the round-1 bracket walk

@@ -10,7 +10,7 @@ constexpr unsigned kKeyGuard = 192u;
 constexpr unsigned kKeyMask = 0xfffffff0u;
 
 // Literal restatement of the reference search for one coordinate (slow path): both bracket ends of every depth,
-// IEEE float32 scores, first maximum in the order left_0..left_N, right_1..right_N.  Returns depth << 16 | index.
+// IEEE float32 scores, first maximum in the order left_0..left_N, right_1..right_N.  Returns depth << 24 | index.
 // sTc = this channel's column of the padded shared-memory tree, sPenc = its penalties (stride pen_stride floats).
 static __device__ __noinline__ int reference_search(const float *sTc, const float *sPenc, int pen_stride, float mu,
                                                     float sg, int N) {
@@ -31,7 +31,34 @@ static __device__ __noinline__ int reference_search(const float *sTc, const floa
         if (sr > bestR) { bestR = sr; nR = n; iR = ir; }
         ip = 2 * ip + b;
     }
-    return bestR > bestL ? (nR << 16 | iR) : (nL << 16 | iL);
+    return bestR > bestL ? (nR << 24 | iR) : (nL << 24 | iL);
+}
+
+// The same for max_bits_per_coord > 10: depths 0..10 from the shared-memory tree, deeper ones from the heap-order table
+// of this channel in global memory (gT[(1 << n) - 1 + i] is code point (n, i)).
+static __device__ __noinline__ int reference_search_deep(const float *sTc, const float *gT, const float *sPenc,
+                                                         int pen_stride, float mu, float sg, int N) {
+    const float rs = rcp_rn(sg);
+    auto point = [&](int n, int i) -> float {
+        return n <= kSmemDepth ? sTc[entry_of(n, i) * VBQ_GROUP] : __ldg(gT + ((1 << n) - 1 + i));
+    };
+    const float z0 = point(0, 0);
+    float bestL = score_exact(z0, mu, sg, rs, -sPenc[0]), bestR = -CUDART_INF_F;
+    int nL = 0, iL = 0, nR = 0, iR = 0;
+    int ip = mu > z0 ? 1 : 0;
+    for (int n = 1; n <= N; ++n) {
+        const float zp = point(n, ip);
+        const int b = mu > zp ? 1 : 0;
+        const int fg = ip + b;
+        const int il = clamp_index(fg, n, N, false), ir = clamp_index(fg, n, N, true);
+        const float npn = -sPenc[n * pen_stride];
+        const float sl = score_exact(il == ip ? zp : point(n, il), mu, sg, rs, npn);
+        const float sr = score_exact(ir == ip ? zp : point(n, ir), mu, sg, rs, npn);
+        if (sl > bestL) { bestL = sl; nL = n; iL = il; }
+        if (sr > bestR) { bestR = sr; nR = n; iR = ir; }
+        ip = 2 * ip + b;
+    }
+    return bestR > bestL ? (nR << 24 | iR) : (nL << 24 | iL);
 }
 
 // Next unclaimed tile of the CTA's current segment: lane 0 increments the shared counter, the warp gets the old value.

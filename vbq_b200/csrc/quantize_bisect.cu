@@ -34,14 +34,19 @@
 // OUT >= 0: the set of requested outputs (bit 0 zhat, 1 qidx, 2 level, 3 bits) is known at compile time; OUT < 0: runtime.
 // VEC: C % 4 == 0 and 16-byte aligned latents: a warp stages its tile (256 B of mu, 256 B of sigma) with ONE 16-byte
 // cp.async per lane; otherwise every thread copies its own two coordinates with 4-byte cp.async.
+// NT < 0 (DEEP): max_bits_per_coord up to VBQ_MAX_DEPTH at run time; the path nodes of depths 11..N come from the
+// heap-order table in global memory (one 4-byte gather per depth; the bracket walk needs up to three), the depth takes
+// 5 key bits instead of 4.
 template <bool PRUNE, bool TOTALS, int NT, int OUT, bool VEC, int kThreads>
 __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) {
     constexpr int U = 2, P = 1;
-    constexpr int kWarps = kThreads / 32;
+    constexpr bool DEEP = NT < 0;
+    constexpr int kKeys = DEEP ? VBQ_MAX_DEPTH + 1 : kSmemDepth + 1;   // candidates (depths) per coordinate
+    constexpr unsigned kDepthBits = DEEP ? 31u : 15u;                   // low key bits that hold the depth
     extern __shared__ __align__(16) float smem[];
     float *sT = smem;                                   // [kPadEntries][16] code points of depths 0..10
-    float *sPen = sT + kPadEntries * VBQ_GROUP;         // [kSmemDepth+1][16] penalties (+inf beyond N)
-    float *sStage = sPen + (kSmemDepth + 1) * VBQ_GROUP;   // [kWarps][kStages][kTileFloats] staging rings
+    float *sPen = sT + kPadEntries * VBQ_GROUP;         // [kKeys][16] penalties (+inf beyond N)
+    float *sStage = sPen + kKeys * VBQ_GROUP;           // [kWarps][kStages][kTileFloats] staging rings
     __shared__ double sRed[VBQ_TOTALS][kMaxThreads / 32];
     __shared__ unsigned sGuard[VBQ_GROUP];
     __shared__ int sNext;                               // next unclaimed tile of the current segment
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
                 const size_t po = ((size_t)lam * a.pen_channels + (a.pen_channels == 1 ? 0 : cj)) * (N + 1);
                 float prev = 0.0f;
                 bool mono = true;   // certified ranking needs 0 <= pen_0 <= pen_1 <= ... (false for NaN)
-                for (int n = 0; n <= kSmemDepth; ++n) {
+                for (int n = 0; n < kKeys; ++n) {
                     const float p = n <= N ? a.pen[po + n] : CUDART_INF_F;
                     mono = mono && (p >= prev);
                     prev = p;
@@ -162,9 +167,10 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
             }
         }
         __syncthreads();
-        float pen[kSmemDepth + 1];
+        float pen[kKeys];
 #pragma unroll
-        for (int n = 0; n <= kSmemDepth; ++n) pen[n] = sPen[n * VBQ_GROUP + col];
+        for (int n = 0; n < kKeys; ++n) pen[n] = sPen[n * VBQ_GROUP + col];
+        const float *gT = a.table + (size_t)cc * a.Q - 1;   // DEEP: heap index K (1-based) -> gT[K]
         const unsigned guard = sGuard[col];
         const float z0 = sTc[entry_of(0, 0) * VBQ_GROUP];
 
@@ -191,12 +197,12 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
                                    make_float2(0.70710678f, 0.70710678f));
             }
 
-            unsigned key[U][kSmemDepth + 1];
+            unsigned key[U][kKeys];
             unsigned K[U];   // 1-based heap index of the path node at the current depth
 #pragma unroll
             for (int u = 0; u < U; ++u)
 #pragma unroll
-                for (int n = 0; n <= kSmemDepth; ++n) key[u][n] = 0x7ffffff0u | (unsigned)n;
+                for (int n = 0; n < kKeys; ++n) key[u][n] = (0x7fffffffu & ~kDepthBits) | (unsigned)n;
 
             // ---- depth 0: the median ---------------------------------------------------------------------
 #pragma unroll
@@ -216,8 +222,10 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
                 constexpr int n = decltype(n_tag)::value;
                 float z[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u)
-                    z[u] = lds_pure((unsigned)(imad((int)K[u], kRowStrideBytes, pbi) + 2 * n * kRowStrideBytes));
+                for (int u = 0; u < U; ++u) {
+                    if (n <= kSmemDepth) z[u] = lds_pure((unsigned)(imad((int)K[u], kRowStrideBytes, pbi) + 2 * n * kRowStrideBytes));
+                    else z[u] = __ldg(gT + K[u]);
+                }
 #pragma unroll
                 for (int k = 0; k < P; ++k) {
                     const float2 d = __fadd2_rn(make_float2(z[2 * k], z[2 * k + 1]), nmu2[k]);
@@ -238,27 +246,41 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
             auto prune_here = [&](auto n_tag) -> bool {
                 constexpr int n = decltype(n_tag)::value;
                 // sound early exit: every deeper loss is >= pen_n, so once the best key plus the guard is below the
-                // key of pen_n no deeper candidate can win or come within the guard
-                const unsigned floor_key = __float_as_uint(pen[n]) & kKeyMask;
-                bool done = guard == kKeyGuard && floor_key > kKeyGuard + 16u;
+                // key of pen_n no deeper candidate can win or come within the guard.  Tested at depths 3, 6, 9 and
+                // before every global-memory depth.
+                const unsigned floor_key = __float_as_uint(pen[n]) & kmask;
+                bool done = guard == kKeyGuard && floor_key > kKeyGuard + 32u;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    run_min[u] = __vimin3_u32(run_min[u], key[u][n - 3], key[u][n - 2]);
-                    run_min[u] = min(run_min[u], key[u][n - 1]);
-                    done = done && run_min[u] < floor_key - (kKeyGuard + 16u);
+                    if (n <= 9) {
+                        run_min[u] = __vimin3_u32(run_min[u], key[u][n - 3], key[u][n - 2]);
+                        run_min[u] = min(run_min[u], key[u][n - 1]);
+                    } else if (n == kSmemDepth + 1) {
+                        run_min[u] = __vimin3_u32(run_min[u], key[u][n - 2], key[u][n - 1]);
+                    } else {
+                        run_min[u] = min(run_min[u], key[u][n - 1]);
+                    }
+                    done = done && run_min[u] < floor_key - (kKeyGuard + 32u);
                 }
                 return __all_sync(0xffffffffu, done);
             };
-#define VBQ_DEPTH(n_)                                                        \
-    if ((NT > 0 ? n_ <= NT : n_ <= N) && !stop) {                            \
-        if (PRUNE && n_ % 3 == 0 && prune_here(std::integral_constant<int, n_>{})) stop = true; \
-        else depth(std::integral_constant<int, n_>{});                       \
+#define VBQ_DEPTH(n_)                                                                                          \
+    if constexpr (n_ <= kSmemDepth || DEEP) {                                                                  \
+        if ((NT > 0 ? n_ <= NT : n_ <= N) && !stop) {                                                          \
+            if (PRUNE && ((n_ <= 9 && n_ % 3 == 0) || n_ > kSmemDepth) &&                                      \
+                prune_here(std::integral_constant<int, n_>{}))                                                 \
+                stop = true;                                                                                   \
+            else                                                                                               \
+                depth(std::integral_constant<int, n_>{});                                                      \
+        }                                                                                                      \
     }
             bool stop = false;
             VBQ_DEPTH(1) VBQ_DEPTH(2) VBQ_DEPTH(3) VBQ_DEPTH(4) VBQ_DEPTH(5)
             VBQ_DEPTH(6) VBQ_DEPTH(7) VBQ_DEPTH(8) VBQ_DEPTH(9) VBQ_DEPTH(10)
+            VBQ_DEPTH(11) VBQ_DEPTH(12) VBQ_DEPTH(13) VBQ_DEPTH(14) VBQ_DEPTH(15)
+            VBQ_DEPTH(16) VBQ_DEPTH(17) VBQ_DEPTH(18) VBQ_DEPTH(19) VBQ_DEPTH(20)
 #undef VBQ_DEPTH
-            static_assert(kSmemDepth == 10, "the depth macro list above covers depths 1..10");
+            static_assert(kSmemDepth == 10 && VBQ_MAX_DEPTH == 20, "the depth macro lists above cover depths 1..10 and 11..20");
             const int kd = (NT > 0 && m_done == NT) ? NT : m_done + 1;   // depth of the node K points at
 
             // ---- winner and certificate -----------------------------------------------------------------------
@@ -267,27 +289,27 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const unsigned *k_ = key[u];
-                unsigned m = __vimin3_u32(k_[0], k_[1], k_[2]);
-                m = __vimin3_u32(m, k_[3], k_[4]);
-                m = __vimin3_u32(m, k_[5], k_[6]);
-                m = __vimin3_u32(m, k_[7], k_[8]);
-                m = __vimin3_u32(m, k_[9], k_[10]);
+                unsigned m = k_[0];
+#pragma unroll
+                for (int n = 1; n + 1 < kKeys; n += 2) m = __vimin3_u32(m, k_[n], k_[n + 1]);
+                if (kKeys % 2 == 0) m = min(m, k_[kKeys - 1]);
                 const unsigned nm = ~m;   // key + ~m = key - m - 1: 0xffffffff for the winner itself
                 unsigned g0 = 0xffffffffu, g1 = 0xffffffffu;   // two chains for instruction-level parallelism
 #pragma unroll
-                for (int n = 0; n <= kSmemDepth; n += 2) g0 = __viaddmin_u32(k_[n], nm, g0);
+                for (int n = 0; n < kKeys; n += 2) g0 = __viaddmin_u32(k_[n], nm, g0);
 #pragma unroll
-                for (int n = 1; n <= kSmemDepth; n += 2) g1 = __viaddmin_u32(k_[n], nm, g1);
+                for (int n = 1; n < kKeys; n += 2) g1 = __viaddmin_u32(k_[n], nm, g1);
                 gapmin = __vimin3_u32(gapmin, g0, g1);
-                wn[u] = (int)(m & 15u);
+                wn[u] = (int)(m & kDepthBits);
                 wP[u] = (int)(K[u] >> (kd - wn[u]));
             }
             if (gapmin <= guard) {   // some coordinate is not certified (or penalties not monotone): literal search
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int r = reference_search(sTc, sPen + col, VBQ_GROUP, mu[u], sg[u], N);
-                    wn[u] = r >> 16;
-                    wP[u] = (1 << wn[u]) + (r & 0xffff);
+                    const int r = DEEP ? reference_search_deep(sTc, gT + 1, sPen + col, VBQ_GROUP, mu[u], sg[u], N)
+                                       : reference_search(sTc, sPen + col, VBQ_GROUP, mu[u], sg[u], N);
+                    wn[u] = r >> 24;
+                    wP[u] = (1 << wn[u]) + (r & 0xffffff);
                 }
             }
             float dist[U];
@@ -303,7 +325,9 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
                     if (outm & 4u) level_c[o] = n;
                     if (outm & 8u) bits_c[o] = (float)n;
                     if (TOTALS || (outm & 1u)) {
-                        const float zh = lds_pure((unsigned)(imad(n, 2 * kRowStrideBytes, imad(Pn, kRowStrideBytes, pbi))));
+                        float zh;
+                        if (DEEP && n > kSmemDepth) zh = __ldg(gT + Pn);
+                        else zh = lds_pure((unsigned)(imad(n, 2 * kRowStrideBytes, imad(Pn, kRowStrideBytes, pbi))));
                         if (outm & 1u) zhat_c[o] = zh;
                         if (TOTALS) {
                             const float r1 = u & 1 ? r2[u / 2].y : r2[u / 2].x;
@@ -364,7 +388,7 @@ static int launch_bisect(QArgs a, int dev, int sms, cudaStream_t st) {
     if (gx > sms) gx = sms;
     if (gx > kMaxGrid) gx = kMaxGrid;
     if (gx < 1) gx = 1;
-    const size_t smem = ((size_t)kPadEntries * VBQ_GROUP + (size_t)(kSmemDepth + 1) * VBQ_GROUP +
+    const size_t smem = ((size_t)kPadEntries * VBQ_GROUP + (size_t)(NT < 0 ? VBQ_MAX_DEPTH + 1 : kSmemDepth + 1) * VBQ_GROUP +
                          (size_t)(T / 32) * kStages * kTileFloats) * sizeof(float);
     auto kern = vbq_bisect_kernel<PRUNE, TOTALS, NT, OUT, VEC, T>;
     VBQ_ENSURE_MAX_SMEM(kern, dev);
@@ -396,8 +420,15 @@ static int launch_bisect2(const QArgs &a, int dev, int sms, cudaStream_t st) {
 
 // raw code lengths (no length table, no entropy model), max_bits_per_coord <= 10; returns -1 if not applicable
 int vbq_launch_quantize_bisect(const QArgs &a, int dev, int sms, cudaStream_t st) {
-    if (a.len || a.em || a.N > kSmemDepth) return -1;
+    if (a.len || a.em) return -1;
     const bool prune = !(a.flags & VBQ_FLAG_NO_PRUNE);
+    if (a.N > kSmemDepth) {   // deep tables: 512 threads (21 keys and penalties per coordinate pair: > 100 registers)
+        QArgs b = a;
+        b.keymask = 0xffffffe0u;
+        const bool tot = a.totals != nullptr;
+        if (prune) return tot ? launch_bisect3<true, true, -1, 512>(b, dev, sms, st) : launch_bisect3<true, false, -1, 512>(b, dev, sms, st);
+        return tot ? launch_bisect3<false, true, -1, 512>(b, dev, sms, st) : launch_bisect3<false, false, -1, 512>(b, dev, sms, st);
+    }
     // 768 threads (24 warps, 80 registers): measured best of 512 / 640 / 768 / 896
     return prune ? launch_bisect2<true, 768>(a, dev, sms, st) : launch_bisect2<false, 768>(a, dev, sms, st);
 }

@@ -215,8 +215,8 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_sweep_kernel(const QAr
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         const int r = reference_search(sTc, sPenL + lam * kPenSlots, 1, mu[u], sg[u], N);
-                        wn[u] = r >> 16;
-                        wP[u] = (1 << wn[u]) + (r & 0xffff);
+                        wn[u] = r >> 24;
+                        wP[u] = (1 << wn[u]) + (r & 0xffffff);
                     }
                 }
                 int t_level = 0;
