@@ -163,6 +163,20 @@ int vbq_compress_coordinates_f64(const float *d_mu, const float *d_sigma, long l
                                  int N, const double *d_lengths, double beta, int pen_f32, float *d_optima,
                                  int *d_heap_index, int *d_level, void *stream);
 
+/* ---- after the search: symbols for an external entropy coder ------------------------------------- */
+
+/* The reference counts its sorted quantile indices per channel (quantizer.py:135-146, np.bincount in a Python loop)
+ * and reports ideal code lengths (ipynb:452-455); it has no wire format.  vbq_symbol_histogram adds, for every
+ * channel c and symbol s < Q = 2^(N+1)-1, the number of rows with d_qidx[r][c] == s to d_counts (C, Q) uint64
+ * (the caller zeroes it; N <= 10).  vbq_pack_indices writes n symbols as a bit stream of N+1 bits per symbol
+ * (symbol k = bits [k(N+1), (k+1)(N+1)), least significant bit first, in little-endian 32-bit words;
+ * vbq_packed_index_words(n, N) words); vbq_unpack_indices is its inverse. */
+long long vbq_packed_index_words(long long n, int N);
+int vbq_pack_indices(const int *d_qidx, long long n, int N, unsigned *d_words, void *stream);
+int vbq_unpack_indices(const unsigned *d_words, long long n, int N, int *d_qidx, void *stream);
+int vbq_symbol_histogram(const int *d_qidx, long long rows, int C, int N, unsigned long long *d_counts,
+                         void *stream);
+
 /* ---- stand-alone operator forms ------------------------------------------------------------------------------- */
 
 /* ChannelwisePriorCDFQuantizer.get_all_N_bit_intervals (quantizer.py:65-80): d_mu (rows, C) -> d_left, d_right

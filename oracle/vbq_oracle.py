@@ -497,3 +497,32 @@ def batch_quantize_indep_dims(P, L, loc, scale, lambs):
         Zh[lamb] = np.take_along_axis(P, k[None], axis=0)[0]
         nb[lamb] = np.take_along_axis(L, k[None], axis=0)[0]
     return Zh, nb
+
+
+# ----------------------------------------------------------------------------------------------
+# Symbol serialisation: fixed-width bit packing and per-channel frequency tables
+# ----------------------------------------------------------------------------------------------
+def pack_indices(q, N):
+    """n symbols of N+1 bits each, symbol k in bits [k(N+1), (k+1)(N+1)) (LSB first) of little-endian uint32 words.
+    Plain-integer restatement of the format documented in include/vbq_b200.h."""
+    q = np.asarray(q).reshape(-1).astype(np.uint64)
+    B = N + 1
+    n_words = (q.size * B + 31) // 32
+    bits = ((q[:, None] >> np.arange(B, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(np.uint8).reshape(-1)
+    bits = np.concatenate([bits, np.zeros(n_words * 32 - bits.size, dtype=np.uint8)])
+    weights = (np.uint64(1) << np.arange(32, dtype=np.uint64))
+    return (bits.reshape(n_words, 32).astype(np.uint64) * weights[None, :]).sum(axis=1).astype(np.uint32)
+
+
+def unpack_indices(words, n, N):
+    B = N + 1
+    w = np.asarray(words).astype(np.uint32)
+    bits = ((w[:, None] >> np.arange(32, dtype=np.uint32)[None, :]) & np.uint32(1)).astype(np.uint64).reshape(-1)
+    bits = bits[:n * B].reshape(n, B)
+    return (bits * (np.uint64(1) << np.arange(B, dtype=np.uint64))[None, :]).sum(axis=1).astype(np.int32)
+
+
+def symbol_histogram(q, Q):
+    """quantizer.py:135-146: per-channel np.bincount of the sorted quantile indices, (rows, C) -> (C, Q)."""
+    q = np.asarray(q)
+    return np.stack([np.bincount(q[:, c], minlength=Q) for c in range(q.shape[1])]).astype(np.int64)

@@ -478,3 +478,49 @@ def compress_coordinates_f64(mu, sigma, codepoints, lengths, beta, pen_f32=True,
                                                   _ptr(index), _ptr(level), _stream(mu.device))
     _lib.check(st, "vbq_compress_coordinates_f64")
     return optima, index, level
+
+
+# ------------------------------------------------------------------------------------------------------
+# after the search: symbols for an external entropy coder (include/vbq_b200.h)
+# ------------------------------------------------------------------------------------------------------
+def packed_index_words(n: int, max_bits: int) -> int:
+    return int(_lib.load().vbq_packed_index_words(int(n), int(max_bits)))
+
+
+def pack_indices(qidx: torch.Tensor, max_bits: int) -> torch.Tensor:
+    """Sorted quantile indices (any shape, int32, CUDA) -> bit stream of max_bits+1 bits per symbol as int32 words."""
+    _need_cuda("qidx", qidx, torch.int32)
+    q = qidx.contiguous().reshape(-1)
+    words = torch.empty(packed_index_words(q.numel(), max_bits), dtype=torch.int32, device=q.device)
+    st = _lib.load().vbq_pack_indices(_ptr(q), q.numel(), max_bits, _ptr(words), _stream(q.device))
+    _lib.check(st, "vbq_pack_indices")
+    return words
+
+
+def unpack_indices(words: torch.Tensor, n: int, max_bits: int) -> torch.Tensor:
+    """Inverse of pack_indices: the first n symbols of the stream as a flat int32 tensor."""
+    _need_cuda("words", words, torch.int32, 1)
+    if words.numel() < packed_index_words(n, max_bits):
+        raise ValueError("vbq_b200: %d words cannot hold %d symbols of %d bits" % (words.numel(), n, max_bits + 1))
+    q = torch.empty(int(n), dtype=torch.int32, device=words.device)
+    st = _lib.load().vbq_unpack_indices(_ptr(words.contiguous()), int(n), max_bits, _ptr(q), _stream(words.device))
+    _lib.check(st, "vbq_unpack_indices")
+    return q
+
+
+def symbol_histogram(qidx: torch.Tensor, max_bits: int, counts: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-channel frequency tables of the sorted quantile indices (rows, C) -> (C, Q) int64 counts
+    (quantizer.py:135-146 builds them with np.bincount per channel).  `counts` accumulates when given."""
+    _need_cuda("qidx", qidx, torch.int32, 2)
+    rows, C = qidx.shape
+    Q = num_levels(max_bits)
+    if counts is None:
+        counts = torch.zeros((C, Q), dtype=torch.int64, device=qidx.device)
+    else:
+        _need_cuda("counts", counts, torch.int64, 2)
+        if tuple(counts.shape) != (C, Q):
+            raise ValueError("vbq_b200: counts must be (C, Q)")
+    st = _lib.load().vbq_symbol_histogram(_ptr(qidx.contiguous()), rows, C, max_bits, _ptr(counts),
+                                          _stream(qidx.device))
+    _lib.check(st, "vbq_symbol_histogram")
+    return counts

@@ -221,6 +221,9 @@ class ChannelwisePriorCDFQuantizer:
         ch = torch.arange(C, device=self.device, dtype=torch.int64)
         counts = []
         for i in range(len(lambs)):
+            if what == 'qidx' and N <= 10:      # shared-memory histogram per 16-channel group (csrc/serialize.cu)
+                counts.append(ops.symbol_histogram(sym[i], N))
+                continue
             flat = (sym[i].to(torch.int64) + ch[None, :] * nbins).reshape(-1)
             counts.append(torch.bincount(flat, minlength=C * nbins).reshape(C, nbins))
         counts = torch.stack(counts)
