@@ -1,4 +1,4 @@
-python -m pytest tests/test_serialize.py -m gpu -q -x 2>&1 | tail -5
+python -m pytest tests -m gpu -q -x 2>&1 | tail -3
 python - <<'PY'
 import torch, time, numpy as np
 from vbq_b200 import ops
