@@ -378,3 +378,36 @@ def test_bisection_sweep_equals_bracket_walk_sweep(N, C, rows, n_lambda):
     assert torch.allclose(a["totals"][:, 3], b["totals"][:, 3], rtol=1e-6, atol=1e-9)
     t = q.quantize(_dev(mu), _dev(sigma), lambs, outputs=ops.OUT_TOTALS)["totals"]     # totals-only path
     assert torch.allclose(t, a["totals"], rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("N,C,rows,n_lambda", [(10, 48, 6000, 16), (10, 21, 1001, 1), (7, 16, 640, 60), (3, 5, 333, 4)])
+@pytest.mark.parametrize("neg", [False, True])
+def test_corrected_lengths_sweep_equals_reference_walk(N, C, rows, n_lambda, neg):
+    """Corrected code lengths (per-channel, not monotone in depth) and the entropy-model gather: the default kernels
+    (bracket-walk sweep, strict single-lambda kernel) vs one literal two-maxima walk per lambda
+    (VBQ_FLAG_NO_SWEEP | VBQ_FLAG_REFERENCE_WALK): identical outputs, one lambda included, with bulk exact hits on code
+    points, lambda = 0, ragged C, and (neg) negative corrections, i.e. negative penalties."""
+    import vbq_b200
+    from vbq_b200 import ops
+    pr = H.make_prior(C, seed=70 + N)
+    q = vbq_b200.ChannelwisePriorCDFQuantizer(C, N)
+    q.set_code_points(ops.build_code_points_learned(_dev(pr.packed()), N))
+    table = q.all_code_points.cpu().numpy()
+    mu, sigma, _ = H.make_latents(pr, rows, 78, table=table)
+    srt = q.code_points_by_channel.cpu().numpy()
+    rng = np.random.default_rng(4)
+    idx = rng.integers(0, srt.shape[1], (rows, C))
+    on = srt[np.arange(C)[None, :], idx]
+    mu = np.where(rng.integers(0, 5, (rows, C)) == 0, on, mu).astype(np.float32)
+    lambs = ([0.0] if n_lambda > 1 else []) + [float(l) for l in 2 ** np.linspace(-8, 7, max(n_lambda - 1, 1))]
+    lo = -3.0 if neg else 0.25
+    q.raw_code_length_entropy_models = {l: rng.uniform(lo, 6.0, (C, N + 1)).astype(np.float32) for l in lambs}
+    q.entropy_models = {l: rng.uniform(0.5, 12.0, (C, q.quantization_levels)).astype(np.float32) for l in lambs}
+    outs = ops.OUT_ZHAT | ops.OUT_QIDX | ops.OUT_LEVEL | ops.OUT_BITS | ops.OUT_TOTALS
+    a = q.quantize(_dev(mu), _dev(sigma), lambs, outputs=outs, entropy_bits=True)
+    b = q.quantize(_dev(mu), _dev(sigma), lambs, outputs=outs, entropy_bits=True,
+                   flags=ops.FLAG_NO_SWEEP | ops.FLAG_REFERENCE_WALK)
+    for k in ("zhat", "qidx", "level", "bits", "em_bits"):
+        assert torch.equal(a[k], b[k]), k
+    assert torch.equal(a["totals"][:, 0], b["totals"][:, 0])
+    assert torch.allclose(a["totals"], b["totals"], rtol=1e-6, atol=1e-6)
