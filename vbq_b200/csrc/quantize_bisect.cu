@@ -24,7 +24,7 @@
 // differ by < 30 as integers.  The depth is embedded in the 4 low bits of the pattern (key_n); the winner is the
 // integer minimum (VIMNMX3), and a second pass (VIADDMNMX) measures the gap to the runner-up.  If the gap exceeds
 // kKeyGuard = 192 > 2*(30+15) the reference's float32 scores are strictly ordered the same way and the result is
-// certified identical; otherwise (about 1 coordinate in 10^4), or when the penalties are not non-decreasing and
+// certified identical; otherwise (3-6 coordinates in 10^5 on Kodak-shaped inputs), or when the penalties are not non-decreasing and
 // non-negative, the coordinate is redone by `reference_search`, the literal two-ended walk with IEEE arithmetic.
 #include <stdlib.h>
 
