@@ -207,16 +207,38 @@ def run_reference(args, rank, world):
     mu, sigma = make_batch_cpu(table, 1000, IMAGES)
     cores = os.cpu_count() or 1
     workers = max(1, min(cores, IMAGES))
-    for _ in range(args.warmup):
-        cpu_throughput(table, mu, sigma, min(IMAGES, workers), workers)
-    vals = []
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        v, _ = cpu_throughput(table, mu, sigma, IMAGES, workers)
-        vals.append(v)
-    total = time.perf_counter() - t0
-    value = IMAGES * H * W * C * args.steps / total
-    sample = "%d Kodak-shaped images per step, one image per call, %d worker processes" % (IMAGES, workers)
+    import multiprocessing as mp
+    per = H * W
+    budget_s = 100.0                       # the whole --steps K run stays within a few minutes whatever K is
+    with mp.get_context("fork").Pool(workers, initializer=_cpu_init, initargs=(table,)) as pool:
+        def run(rows_per_job, n_jobs):
+            jobs = [(mu[(i % IMAGES) * per:(i % IMAGES) * per + rows_per_job],
+                     sigma[(i % IMAGES) * per:(i % IMAGES) * per + rows_per_job]) for i in range(n_jobs)]
+            t0 = time.perf_counter()
+            pool.map(_cpu_one_image, jobs, chunksize=1)
+            return time.perf_counter() - t0
+        run(per, workers)                  # warm the workers (search grids, caches)
+        t_img = run(per, workers)          # one image per worker
+        for _ in range(max(0, args.warmup - 2)):
+            run(per, workers)
+        # a step is a bounded sample of the workload: whole images (one per call, like utils.py:535-542) while they fit
+        # the per-step share of the budget, otherwise the first rows of one image per worker
+        share = budget_s / max(args.steps, 1)
+        if share >= t_img:
+            n_jobs = int(min(IMAGES, workers * max(1, int(share / t_img))))
+            rows_per_job = per
+        else:
+            n_jobs = workers
+            rows_per_job = int(max(64, per * share / t_img))
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            run(rows_per_job, n_jobs)
+        total = time.perf_counter() - t0
+    coords_per_step = n_jobs * rows_per_job * C
+    value = coords_per_step * args.steps / total
+    sample = "%d jobs of %d rows x %d channels per step (%s), one call per job, %d worker processes" % (
+        n_jobs, rows_per_job, C, "whole Kodak-shaped images" if rows_per_job == per else "leading rows of an image",
+        workers)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
@@ -411,7 +433,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--flags", type=int, default=0, help="VBQ_FLAG_* bits passed to vbq_quantize")
