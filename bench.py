@@ -284,8 +284,6 @@ def run_ours(args, rank, world, local_rank):
     # rotating buffer sets so that no step finds its inputs in the 126 MB L2
     set_bytes = COORDS * BYTES_PER_COORD
     n_sets = max(3, -(-3 * L2_BYTES // set_bytes))
-    if os.environ.get("VBQ_SETS"):            # development only: 1 = inputs stay in L2 (NOT a valid bench line)
-        n_sets = int(os.environ["VBQ_SETS"])
     sets = []
     for s in range(n_sets):
         mu, sigma = make_batch(prior, 1000 + 17 * rank + s, dev)
