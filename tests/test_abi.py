@@ -103,3 +103,22 @@ def test_host_helpers():
     assert np.array_equal(np.argsort(np.argsort(utils.all_bin_floats(N))), utils.heap_to_sorted_index(n, i, N))
     f = utils.curry_normal_logpdf(loc=torch.tensor([1.0]), scale=torch.tensor([2.0]), ignore_const=True)
     assert float(f(torch.tensor([3.0]))) == -0.5
+
+
+def test_span_cuts_partition_every_tile_exactly_once():
+    """The work split of the bisection kernels (same host/device function): monotone cuts from 0 to the tile count,
+    balanced within the group-switch charge, for ragged shapes and grids larger than the work."""
+    from vbq_b200 import _lib
+    lib = _lib.load()
+    for rows, C, grid in ((36864, 192, 148), (36864, 192, 147), (1, 1, 148), (5, 33, 7), (1000003, 300, 148),
+                          (64, 320, 1), (0, 16, 4), (4097, 17, 1024)):
+        out = (ctypes.c_longlong * (grid + 1))()
+        assert lib.vbq_selftest_span_cuts(rows, C, grid, out) == 0
+        cuts = list(out)
+        tiles = ((rows + 3) // 4) * ((C + 15) // 16)
+        assert cuts[0] == 0 and cuts[-1] == tiles
+        assert all(a <= b for a, b in zip(cuts, cuts[1:]))
+        sizes = [b - a for a, b in zip(cuts, cuts[1:])]
+        if tiles >= 100 * grid:
+            assert max(sizes) - min(sizes) <= 81 + 1           # a CTA that crosses a group boundary gets up to 80 fewer
+    assert lib.vbq_selftest_span_cuts(8, 0, 4, (ctypes.c_longlong * 5)()) == 2

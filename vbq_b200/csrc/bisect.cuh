@@ -96,10 +96,11 @@ constexpr int kTileFloats = 2 * kTileRows * VBQ_GROUP;   // mu rows then sigma r
 constexpr int kSwitchTiles = 80;   // measured: a second segment costs a CTA about 2.8 us = 50-80 tiles
 
 // first real tile (in group-major order) of virtual position v: every group is preceded by kSwitchTiles virtual tiles
-__device__ __forceinline__ long long span_cut(long long v, long long tiles_per_group, int n_groups) {
+__host__ __device__ __forceinline__ long long span_cut(long long v, long long tiles_per_group, int n_groups) {
     const long long vg = tiles_per_group + kSwitchTiles;
-    const long long g = min(v / vg, (long long)n_groups);
+    long long g = v / vg;
+    if (g > n_groups) g = n_groups;
     const long long o = v - g * vg;
-    return g * tiles_per_group + max(0ll, o - kSwitchTiles);
+    return g * tiles_per_group + (o > kSwitchTiles ? o - kSwitchTiles : 0);
 }
 

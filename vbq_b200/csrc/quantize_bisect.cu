@@ -432,3 +432,14 @@ int vbq_launch_quantize_bisect(const QArgs &a, int dev, int sms, cudaStream_t st
     // 768 threads (24 warps, 80 registers): measured best of 512 / 640 / 768 / 896
     return prune ? launch_bisect2<true, 768>(a, dev, sms, st) : launch_bisect2<false, 768>(a, dev, sms, st);
 }
+
+// Self-test helper (host only, no GPU): the tile range [out[b], out[b+1]) CTA b of a `grid`-CTA launch takes, for
+// `rows` rows and C channels — the same span_cut arithmetic the kernels run.
+extern "C" int vbq_selftest_span_cuts(long long rows, int C, int grid, long long *out) {
+    if (rows < 0 || C < 1 || grid < 1 || !out) return vbq_fail(VBQ_ERR_BAD_SHAPE, "vbq_selftest_span_cuts: bad argument");
+    const long long tpg = (rows + kTileRows - 1) / kTileRows;
+    const int n_groups = (C + VBQ_GROUP - 1) / VBQ_GROUP;
+    const long long vtotal = (tpg + kSwitchTiles) * n_groups;
+    for (int b = 0; b <= grid; ++b) out[b] = span_cut(vtotal * b / grid, tpg, n_groups);
+    return VBQ_OK;
+}
