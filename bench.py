@@ -8,7 +8,8 @@ A "step" is one pass of the hot path over one batch: the Kodak-shaped bls2017 la
 configs[1] (24 images x 32x48 x 192 channels = 7,077,888 coordinates, learned factorized prior at reference init,
 max_bits_per_coord=10, single lambda=0.5), written out as sorted quantile index (int32) + code length (float32)
 per coordinate, plus the per-lambda rate/distortion totals.  With N>1 every rank processes its own batch of that
-shape (weak scaling, no data-path collective) and the totals are all-reduced over NCCL inside the timed region.
+shape (weak scaling, no data-path collective) and the totals are all-reduced over NCCL inside the timed region
+(the totals of four consecutive steps per collective).
 
 `value` is device-resident throughput (CUDA events, max over ranks); `e2e` goes through the reference-facing
 ChannelwisePriorCDFQuantizer.compress_batch_channel_latents-level call with pinned HOST buffers (H2D and D2H
@@ -290,33 +291,42 @@ def run_ours(args, rank, world, local_rank):
         sets.append(dict(mu=mu, sigma=sigma,
                          qidx=torch.empty((1, ROWS, C), dtype=torch.int32, device=dev),
                          bits=torch.empty((1, ROWS, C), dtype=torch.float32, device=dev)))
-    # one validated plan per buffer set: a step is one prebound vbq_quantize call (one kernel launch incl. totals); the
-    # NCCL all-reduce of step i (asynchronous, on NCCL's own stream) overlaps the kernel of step i+1, and a set is
-    # reused only after the all-reduce of its previous totals has finished (all inside the timed region)
-    plans = []
-    for b in sets:
-        b["totals"] = torch.zeros((1, 4), dtype=torch.float64, device=dev)
-        plans.append(ops.QuantizePlan(b["mu"], b["sigma"], q.all_code_points, q._packed, pen, length, None, N_BITS,
-                                      qidx=b["qidx"], bits=b["bits"], totals=b["totals"], flags=args.flags,
-                                      graph=args.graph))
-    totals = sets[0]["totals"]
-    pending = [None] * n_sets
+    # one validated plan per (totals bucket, buffer set): a step is one prebound vbq_quantize call (one kernel launch
+    # incl. totals).  N > 1: the totals of n_sets consecutive steps form one bucket that is all-reduced with ONE NCCL call
+    # (asynchronous, on NCCL's own stream, overlapping the kernels of the next bucket); two buckets alternate, and a
+    # bucket is reused only after its previous all-reduce has finished (all inside the timed region).  Bucketing keeps
+    # most kernel boundaries free of stream operations, so that consecutive launches overlap (programmatic dependent
+    # launch) as they do on one GPU.
+    n_buckets = 2 if world > 1 else 1
+    buckets = [torch.zeros((n_sets, 1, 4), dtype=torch.float64, device=dev) for _ in range(n_buckets)]
+    plans = [[ops.QuantizePlan(b["mu"], b["sigma"], q.all_code_points, q._packed, pen, length, None, N_BITS,
+                               qidx=b["qidx"], bits=b["bits"], totals=buckets[k][s], flags=args.flags,
+                               graph=args.graph) for s, b in enumerate(sets)] for k in range(n_buckets)]
+    pending = [None] * n_buckets
+    last = {"i": -1}
 
     def step(i):
-        s_ = i % n_sets
-        if pending[s_] is not None:
-            pending[s_].wait()
-            pending[s_] = None
-        t = plans[s_].run()
-        if world > 1:
-            pending[s_] = dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)
+        last["i"] = i
+        k, s_ = (i // n_sets) % n_buckets, i % n_sets
+        if s_ == 0 and pending[k] is not None:
+            pending[k].wait()
+            pending[k] = None
+        t = plans[k][s_].run()
+        if world > 1 and s_ == n_sets - 1:
+            pending[k] = dist.all_reduce(buckets[k], op=dist.ReduceOp.SUM, async_op=True)
         return t
 
     def drain():
-        for s_ in range(n_sets):
-            if pending[s_] is not None:
-                pending[s_].wait()
-                pending[s_] = None
+        if world > 1:
+            for k in range(n_buckets):
+                if pending[k] is not None:
+                    pending[k].wait()
+                    pending[k] = None
+            # a partially filled last bucket (the run did not end on a bucket boundary) is reduced here
+            i = last["i"]
+            if i >= 0 and i % n_sets != n_sets - 1:
+                dist.all_reduce(buckets[(i // n_sets) % n_buckets], op=dist.ReduceOp.SUM)
+                last["i"] = -1
 
     def barrier():
         if world > 1:
@@ -413,7 +423,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD, "coords_per_step_per_gpu": COORDS, "max_bits_per_coord": N_BITS,
                    "lambdas": [LAMB], "outputs": "sorted quantile index int32 + code length f32 + totals",
                    "l2": "%d rotating input/output sets (%d MB) > 126 MB L2" % (n_sets, n_sets * set_bytes >> 20),
-                   "flags": args.flags, "parallelism": "dp%d, one all-reduce of (n_lambda,4) f64 totals" % world},
+                   "flags": args.flags, "parallelism": "dp%d, totals (n_lambda,4) f64 all-reduced over NCCL in buckets of %d steps" % (world, n_sets)},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
                      "kernel": "vbq_bisect_kernel", "kernel_ms": kern_ms,
