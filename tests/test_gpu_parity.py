@@ -411,3 +411,33 @@ def test_corrected_lengths_sweep_equals_reference_walk(N, C, rows, n_lambda, neg
         assert torch.equal(a[k], b[k]), k
     assert torch.equal(a["totals"][:, 0], b["totals"][:, 0])
     assert torch.allclose(a["totals"], b["totals"], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_quantize_plan_repeats_the_call(graph):
+    """ops.QuantizePlan (validated once, prebound C call or CUDA-graph replay, zeroed-workspace flag, programmatic
+    dependent launch between back-to-back runs) returns exactly what the one-shot op returns, run after run."""
+    import vbq_b200
+    from vbq_b200 import ops
+    C, N, rows = 32, 10, 4100
+    pr = H.make_prior(C, seed=91)
+    q = vbq_b200.ChannelwisePriorCDFQuantizer(C, N)
+    q.set_code_points(ops.build_code_points_learned(_dev(pr.packed()), N))
+    mu, sigma, _ = H.make_latents(pr, rows, 92, table=q.all_code_points.cpu().numpy())
+    mu_d, sg_d = _dev(mu), _dev(sigma)
+    for lambs in ([0.5], [2.0 ** -6, 0.5, 8.0]):
+        want = q.quantize(mu_d, sg_d, lambs, outputs=ops.OUT_QIDX | ops.OUT_BITS | ops.OUT_TOTALS)
+        pen, length = q._length_tables(lambs)
+        L = len(lambs)
+        qidx = torch.empty((L, rows, C), dtype=torch.int32, device="cuda")
+        bits = torch.empty((L, rows, C), dtype=torch.float32, device="cuda")
+        totals = torch.zeros((L, 4), dtype=torch.float64, device="cuda")
+        plan = ops.QuantizePlan(mu_d, sg_d, q.all_code_points, q._packed, pen, length, None, N, qidx=qidx, bits=bits,
+                                totals=totals, flags=ops.search_flags(lambs), graph=graph)
+        for _ in range(5):
+            qidx.fill_(-1)
+            t = plan.run()
+            plan.run()                      # back to back: the second launch overlaps the first one's tail
+        torch.cuda.synchronize()
+        assert torch.equal(qidx, want["qidx"]) and torch.equal(bits, want["bits"])
+        assert torch.equal(t, want["totals"])
