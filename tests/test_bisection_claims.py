@@ -118,3 +118,32 @@ def test_share_of_uncertified_coordinates_on_bench_shaped_inputs():
         shares[lam] = float(((two[1] - two[0] - 1) <= 192).mean())
     print("uncertified share:", shares)
     assert all(v < 2e-3 for v in shares.values())
+
+
+def test_certified_winner_equals_reference_winner():
+    """End-to-end model of the kernel's decision in NumPy: integer keys of the approximate losses of the path nodes,
+    winner = minimum, certificate = gap to the runner-up > 192.  Every certified coordinate must carry the oracle's
+    depth and code point — on inputs where a third of the coordinates sit on code points or exactly between two — and
+    the reciprocal may be off by an ulp either way."""
+    total = cert = 0
+    for (C, N, rows, seed) in ((24, 10, 4000, 21), (9, 7, 3000, 22)):
+        table, mu, sigma, oq = _setup(C, N, rows, seed)
+        nodes = path_nodes(table, mu)
+        lambs = [0.0, 2.0 ** -8, 0.1, 0.5, 3.0, 16.0]
+        Zo, Bo = oq.compress_batch_channel_latents(mu, sigma, lambs)
+        for l in lambs:
+            pen = ((F32(l) * np.arange(N + 1, dtype=F32))[:, None, None] * np.ones_like(nodes)).astype(F32)
+            for ulps in (-1, 0, 1):
+                _, A = _keys(nodes, mu[None], sigma[None], pen, ulps)
+                keys = (A & ~np.int64(15)) | np.arange(N + 1, dtype=np.int64)[:, None, None]
+                order = np.sort(keys, axis=0)
+                winner = (order[0] & 15).astype(np.int64)
+                certified = (order[1] - order[0] - 1 > 192) if N > 0 else np.ones_like(winner, dtype=bool)
+                certified &= np.isfinite(A.astype(np.int32).view(F32)).all(axis=0)
+                z_w = np.take_along_axis(nodes, winner[None], axis=0)[0]
+                assert np.array_equal(winner[certified], Bo[l][certified].astype(np.int64)), (l, ulps)
+                assert np.array_equal(z_w[certified], Zo[l][certified]), (l, ulps)
+                total += certified.size
+                cert += int(certified.sum())
+    print("certified %d of %d (coordinate, lambda, rcp error) cases; the rest take the literal search" % (cert, total))
+    assert cert > 0.6 * total
