@@ -14,7 +14,9 @@
  *                  — quantizer.py:30-36 `all_code_points`; the notebook's `codepoints` (ipynb:383-390) is one row
  *   packed table   ceil(C/16) groups x 2069 entries x 16 channels, the shared-memory image of a 16-channel group:
  *                  bit depths 0..10, each stored as [pad, 2^n points, pad] so bracket ends need no clamping;
- *                  made by vbq_pack_code_points
+ *                  followed by ceil(C/16) "walk trees" of 40960 floats (the same code points in heap order, scaled by
+ *                  2^24, bit depths 1..7 twice: the shared-memory image of vbq_bisect_tma_kernel); made by
+ *                  vbq_pack_code_points, vbq_packed_table_floats(C, N) floats in all
  *   prior params   (C, 43) float32: for layer k=0..3: matrix (d_{k+1} x d_k row-major), bias (d_{k+1}),
  *                  factor (d_{k+1}, k<3), dims (1,3,3,3,1), already softplus/tanh-transformed
  *                  — learned_prior.py:30-58 `_matrices`, `_biases`, `_factors`
@@ -59,6 +61,8 @@ enum {
                                          ticket counters) are zero: true after a cudaMemset at allocation and after every
                                          completed call, which leaves them zero again.  Saves the per-call memset node
                                          (about 5 us of stream time on a B200). */
+#define VBQ_FLAG_NO_TMA 512u           /* single lambda: stage the latents with per-warp cp.async (vbq_bisect_kernel) instead
+                                         of the TMA pipeline (vbq_bisect_tma_kernel); same results, for comparison */
 #define VBQ_FLAG_BRACKET_WALK 128u     /* single lambda: use the nearer-bracket-end walk (strict mode) even where the
                                          certified bisection kernel applies (same results; for comparison) */
 #define VBQ_FLAG_REFERENCE_WALK 32u   /* score both bracket ends of every depth (the slower, literal formulation; same results) */
@@ -122,6 +126,18 @@ int vbq_quantize(const float *d_mu, const float *d_sigma, long long rows, int C,
                  float *d_zhat, int *d_qidx, int *d_level, float *d_bits, float *d_em_bits,
                  double *d_totals, void *d_workspace, long long workspace_bytes,
                  unsigned flags, void *stream);
+
+/* vbq_quantize with an additional HOST copy of the penalties (same shape and values as d_penalty; may be NULL).  The
+ * reference forms lambda * code_length on the host (utils.py:393-396), so its caller always has them; when they do
+ * not depend on the channel (raw code lengths, quantizer.py:166-169) and n_lambda == 1 the search kernel takes them
+ * as launch constants instead of spending a register per bit depth on them.  Results are identical. */
+int vbq_quantize_hp(const float *d_mu, const float *d_sigma, long long rows, int C,
+                    const float *d_table, const float *d_packed, int N,
+                    const float *d_penalty, const float *h_penalty, const float *d_length, int n_lambda,
+                    int pen_channels, const float *d_entropy_model,
+                    float *d_zhat, int *d_qidx, int *d_level, float *d_bits, float *d_em_bits,
+                    double *d_totals, void *d_workspace, long long workspace_bytes,
+                    unsigned flags, void *stream);
 
 /* ---- the hot path for host-resident latents ---------------------------------------------------------------- */
 

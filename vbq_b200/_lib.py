@@ -19,6 +19,7 @@ FLAG_REFERENCE_WALK = 32
 FLAG_RESERVE_SM = 64
 FLAG_BRACKET_WALK = 128
 FLAG_WORKSPACE_ZEROED = 256
+FLAG_NO_TMA = 512
 GROUP = 16
 TOTALS = 4
 PRIOR_PARAMS = 43
@@ -51,6 +52,8 @@ SIGNATURES = {
     "vbq_quantize_workspace_bytes": (_ll, [_i]),
     "vbq_quantize": (_i, [_p, _p, _ll, _i, _p, _p, _i, _p, _p, _i, _i, _p,
                           _p, _p, _p, _p, _p, _p, _p, _ll, _u, _p]),
+    "vbq_quantize_hp": (_i, [_p, _p, _ll, _i, _p, _p, _i, _p, _p, _p, _i, _i, _p,
+                             _p, _p, _p, _p, _p, _p, _p, _ll, _u, _p]),
     "vbq_host_ctx_create": (_i, [_i, _i, _i, _ll, _u, C.POINTER(C.c_void_p)]),
     "vbq_host_ctx_destroy": (_i, [_p]),
     "vbq_quantize_host": (_i, [_p, _p, _p, _ll, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _u]),

@@ -52,6 +52,36 @@ __global__ void pack_table_kernel(const float *__restrict__ table, int C, int N,
 }
 
 
+// ------------------------------------------------------------------------------------------------------------
+// walk tree of vbq_bisect_tma_kernel (quantize_tma.cu): per group [2048][16] floats in heap order (row K = node K,
+// children 2K and 2K+1, row 0 unused) followed by [256][2][16]: rows K < 256 again, twice (one copy per half-warp);
+// every value scaled by 2^24; unused depths (> N) repeat the ancestor at depth N
+// ------------------------------------------------------------------------------------------------------------
+__global__ void pack_walk_tree_kernel(const float *__restrict__ table, int C, int N, int Q, int n_groups,
+                                      float *__restrict__ walk) {
+    const int per_group = (int)(vbq_walk_tree_floats(1));
+    const int single = (1 << VBQ_SMEM_LEVELS) * VBQ_GROUP;
+    const long long total = (long long)n_groups * per_group;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+        const int g = (int)(t / per_group);
+        const int o = (int)(t - (long long)g * per_group);
+        const int j = o % VBQ_GROUP;
+        int K = o < single ? o / VBQ_GROUP : (o - single) / (2 * VBQ_GROUP);
+        float v = 0.0f;
+        if (K >= 1) {
+            int n = 31 - __clz(K);
+            while (n > N) {
+                --n;
+                K >>= 1;
+            }
+            const int c = min(g * VBQ_GROUP + j, C - 1);
+            v = table[(size_t)c * Q + (K - 1)] * 16777216.0f;
+        }
+        walk[t] = v;
+    }
+}
+
 __global__ void selftest_divide_kernel(const float *__restrict__ x, const float *__restrict__ y, long long n,
                                        float *__restrict__ out) {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -65,7 +95,7 @@ __global__ void selftest_divide_kernel(const float *__restrict__ x, const float 
 extern "C" long long vbq_packed_table_floats(int C, int N) {
     if (C < 1 || N < 0 || N > VBQ_MAX_DEPTH) return -1;
     const long long groups = (C + VBQ_GROUP - 1) / VBQ_GROUP;
-    return groups * kPadEntries * VBQ_GROUP;
+    return groups * kPadEntries * VBQ_GROUP + vbq_walk_tree_floats((int)groups);
 }
 
 extern "C" int vbq_pack_code_points(const float *d_table, int C, int N, float *d_packed, void *stream) {
@@ -80,6 +110,10 @@ extern "C" int vbq_pack_code_points(const float *d_table, int C, int N, float *d
     RETURN_IF(vbq_grid_for((long long)groups * kPadEntries * VBQ_GROUP, 256, &grid));
     pack_table_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_table, C, N, Q, groups, d_packed);
     CUDA_TRY(cudaGetLastError());
+    RETURN_IF(vbq_grid_for(vbq_walk_tree_floats(groups), 256, &grid));
+    pack_walk_tree_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_table, C, N, Q, groups,
+                                                                 d_packed + (size_t)groups * kPadEntries * VBQ_GROUP);
+    CUDA_TRY(cudaGetLastError());
     return VBQ_OK;
 }
 
@@ -93,12 +127,24 @@ extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long r
                             int pen_channels, const float *d_entropy_model, float *d_zhat, int *d_qidx, int *d_level,
                             float *d_bits, float *d_em_bits, double *d_totals, void *d_workspace,
                             long long workspace_bytes, unsigned flags, void *stream) {
+    return vbq_quantize_hp(d_mu, d_sigma, rows, C, d_table, d_packed, N, d_penalty, nullptr, d_length, n_lambda,
+                           pen_channels, d_entropy_model, d_zhat, d_qidx, d_level, d_bits, d_em_bits, d_totals,
+                           d_workspace, workspace_bytes, flags, stream);
+}
+
+extern "C" int vbq_quantize_hp(const float *d_mu, const float *d_sigma, long long rows, int C, const float *d_table,
+                               const float *d_packed, int N, const float *d_penalty, const float *h_penalty,
+                               const float *d_length, int n_lambda, int pen_channels, const float *d_entropy_model,
+                               float *d_zhat, int *d_qidx, int *d_level, float *d_bits, float *d_em_bits,
+                               double *d_totals, void *d_workspace, long long workspace_bytes, unsigned flags,
+                               void *stream) {
     if (rows < 0 || C < 1 || n_lambda < 1 || n_lambda > 65535 || (pen_channels != 1 && pen_channels != C))
         return vbq_fail(VBQ_ERR_BAD_SHAPE, "vbq_quantize: rows=%lld C=%d n_lambda=%d pen_channels=%d", rows, C,
                         n_lambda, pen_channels);
     RETURN_IF(vbq_check_depth(N));
     if (flags & ~(VBQ_FLAG_LOGVAR | VBQ_FLAG_NO_PRUNE | VBQ_FLAG_FAST | VBQ_FLAG_ACCUMULATE_TOTALS | VBQ_FLAG_NO_SWEEP |
-                  VBQ_FLAG_REFERENCE_WALK | VBQ_FLAG_RESERVE_SM | VBQ_FLAG_BRACKET_WALK | VBQ_FLAG_WORKSPACE_ZEROED))
+                  VBQ_FLAG_REFERENCE_WALK | VBQ_FLAG_RESERVE_SM | VBQ_FLAG_BRACKET_WALK | VBQ_FLAG_WORKSPACE_ZEROED |
+                  VBQ_FLAG_NO_TMA))
         return vbq_fail(VBQ_ERR_BAD_FLAGS, "vbq_quantize: unknown flag bits 0x%x", flags);
     if (!d_table || !d_packed || !d_penalty || (rows > 0 && (!d_mu || !d_sigma)))
         return vbq_fail(VBQ_ERR_NULL_POINTER, "vbq_quantize: null input pointer");
@@ -112,7 +158,7 @@ extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long r
     a.mu = d_mu; a.sigma = d_sigma; a.rows = rows; a.C = C;
     a.table = d_table; a.packed = d_packed;
     a.N = N; a.Q = (1 << (N + 1)) - 1;
-    a.pen = d_penalty; a.len = d_length; a.n_lambda = n_lambda; a.pen_channels = pen_channels;
+    a.pen = d_penalty; a.h_pen = h_penalty; a.len = d_length; a.n_lambda = n_lambda; a.pen_channels = pen_channels;
     a.em = d_entropy_model;
     a.zhat = d_zhat; a.qidx = d_qidx; a.level = d_level; a.bits = d_bits; a.em_bits = d_em_bits;
     a.totals = d_totals; a.partials = nullptr; a.ticket = nullptr;
@@ -173,7 +219,8 @@ extern "C" int vbq_quantize(const float *d_mu, const float *d_sigma, long long r
         else if (flags & VBQ_FLAG_REFERENCE_WALK) st_ = vbq_launch_quantize_reference(b, dev, sms, st);
         else {
             // default: certified bisection (raw code lengths, N <= 10); otherwise the bracket walk in strict mode
-            st_ = (flags & VBQ_FLAG_BRACKET_WALK) ? -1 : vbq_launch_quantize_bisect(b, dev, sms, st);
+            st_ = (flags & (VBQ_FLAG_BRACKET_WALK | VBQ_FLAG_NO_TMA)) ? -1 : vbq_launch_quantize_tma(b, dev, sms, st);
+            if (st_ < 0) st_ = (flags & VBQ_FLAG_BRACKET_WALK) ? -1 : vbq_launch_quantize_bisect(b, dev, sms, st);
             if (st_ < 0) st_ = vbq_launch_quantize_strict(b, dev, sms, st);
         }
         RETURN_IF(st_);

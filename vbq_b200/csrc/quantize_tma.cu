@@ -1,0 +1,611 @@
+// quantize_tma.cu — the single-lambda certified bisection (quantize_bisect.cu explains the search and why its result is
+// the reference's) as a warp-specialised TMA pipeline for sm_100a.
+//
+// Reference behaviour reproduced (paths relative to mandt-lab/vbq): img-compression/quantizer.py:65-80, :156-188 and
+// img-compression/utils.py:318-320, :392-415 — identical results to vbq_bisect_kernel; data movement, the tree walk and
+// the work decomposition differ.
+//
+// Structure.  One persistent CTA per SM: W consumer warps + one producer warp (one elected lane).
+//   * tile = W quads; a quad = 4 consecutive rows x the 16 channels of one group = one warp iteration (lane = (row
+//     parity, channel), two coordinates per thread: rows parity and parity + 2).  Warp w ALWAYS computes quad w of a
+//     tile: nothing is claimed, the thread -> coordinate map is static, so every thread adds its distortion terms in a
+//     fixed order and the totals are bit-reproducible.
+//   * the producer brings the mu box and the sigma box of a tile (4W rows x 16 channels, 64-byte rows) into one of S
+//     shared-memory slots with two cp.async.bulk.tensor loads (TMA) that complete on the slot's `full` mbarrier.  The
+//     consumers read their coordinates from the slot, search, and write the two outputs BACK INTO THE SAME slot words
+//     (a thread only ever touches its own words); after fence.proxy.async + one arrive per warp on the slot's `done`
+//     mbarrier the producer sends the slot to global memory with two TMA stores and refills it.  No consumer thread
+//     computes a global address, tests a bound or issues a global load / store for the latents and the outputs.
+//   * the CTA's share of the work is a contiguous range of rows (multiples of 4) in (group, row) order; the last tile of
+//     a range is cut to its rows: its quads beyond the cut are skipped and its outputs leave through 4-row boxes.
+//   * the group's code points arrive by ONE plain bulk copy (UBLKCP, 160 KB) in the "walk tree" layout made by
+//     pack_walk_tree_kernel (quantize.cu): heap order (node K has children 2K, 2K+1), every value scaled by 2^24,
+//     rows of 16 channels; bit depths 1..7 a second time with rows of 32 words = one private copy per half-warp, so a
+//     tree load of these depths touches 32 different banks (the single copy costs two wavefronts per load: the two
+//     half-warps of a warp hit the same 16 banks whenever their path bits agree).
+//   * the walk runs on the FMA pipe.  The shared-memory BYTE ADDRESS of the path node is kept as a float whose bit
+//     pattern is that address — a subnormal number, on which FMA arithmetic is exact integer arithmetic up to 2^24 —:
+//     addr' = 2 addr + stride [mu > z] - base  is  fma(step, stride, fma(addr, 2, -base))  with
+//     step = sat(-(z - mu) * 2^127) in {0, 1} (FMUL.SAT; the 2^24 scaling of the tree and of mu makes every non-zero
+//     difference at least 2^-125, so the product saturates).  The integer pipe (2 cycles per warp instruction, the
+//     saturated unit of vbq_bisect_kernel) keeps only the keys, the minimum and the certificate.
+#include <math.h>
+#include <stdlib.h>
+
+#include "bisect.cuh"
+#include "tma.cuh"
+
+constexpr int kQuadRows = 4;
+constexpr int kSlots = 4;                  // tiles in flight per CTA
+constexpr int kDblDepth = 7;               // bit depths 1..kDblDepth also exist as one copy per half-warp
+constexpr int kSingleRows = 1 << (kSmemDepth + 1);               // heap index K = 1 .. 2047, row 0 unused
+constexpr int kDblRows = 1 << (kDblDepth + 1);                   // K = 2 .. 255, rows 0 and 1 unused
+constexpr int kWalkFloats = kSingleRows * VBQ_GROUP + kDblRows * 2 * VBQ_GROUP;   // 40960 floats = 160 KB per group
+constexpr float kWalkScale = 16777216.0f;                        // 2^24
+constexpr float kWalkUnscale = 1.0f / 16777216.0f;
+constexpr long long kSwitchRows = 320;     // a second range (new tree) costs a CTA about as much as this many rows
+
+struct TmaMaps {
+    CUtensorMap in[2];       // mu, sigma: box of 4W rows
+    CUtensorMap out[2][2];   // [first, second output array of the compiled output set][0: 4W-row box, 1: 4-row box]
+};
+
+struct UniformPen { float v[kSmemDepth + 1]; };   // warp-uniform penalties as launch constants (constant bank operands)
+
+// first real row position (group-major: position = group * rows4 + row) of virtual position v: every group but the
+// first is preceded by kSwitchRows virtual rows — what a second range (drain, new tree, refill) costs the CTA whose
+// share crosses the group boundary; the first tree load is the same for every CTA
+__host__ __device__ __forceinline__ long long row_cut(long long v, long long rows4, int n_groups) {
+    const long long vg = rows4 + kSwitchRows;
+    long long g = (v + kSwitchRows) / vg;
+    if (g > n_groups) g = n_groups;
+    const long long o = v + kSwitchRows - g * vg;
+    return g * rows4 + (o > kSwitchRows ? (o - kSwitchRows) & ~3ll : 0);
+}
+
+#ifdef VBQ_TRACE   // development: %globaltimer stamps into the workspace behind the partial totals (scripts/trace_tma.py)
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TRACE_P(tile, k) do { if ((tile) < 64) tr[8 + (tile) * 4 + (k)] = (double)gtime(); } while (0)
+#define TRACE_C(tile, k) do { if (lane == 0 && (tile) < 64 && tw >= 0) tr[264 + (tw * 64 + (tile)) * 3 + (k)] = (double)gtime(); } while (0)
+#else
+#define TRACE_P(tile, k) do {} while (0)
+#define TRACE_C(tile, k) do {} while (0)
+#endif
+
+__device__ __forceinline__ float mul_sat(float a, float b) {
+    float r;
+    asm("mul.rn.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+// the literal search (slow path) on the walk tree: code point (n, i) = single[(2^n + i) * 16 + c] / 2^24
+static __device__ __noinline__ int reference_search_walk(const float *sSc, const float *sPen, float mu, float sg, int N) {
+    const float rs = rcp_rn(sg);
+    auto point = [&](int n, int i) -> float { return sSc[((1 << n) + i) * VBQ_GROUP] * kWalkUnscale; };
+    const float z0 = point(0, 0);
+    float bestL = score_exact(z0, mu, sg, rs, -sPen[0]), bestR = -CUDART_INF_F;
+    int nL = 0, iL = 0, nR = 0, iR = 0;
+    int ip = mu > z0 ? 1 : 0;
+    for (int n = 1; n <= N; ++n) {
+        const float zp = point(n, ip);
+        const int b = mu > zp ? 1 : 0;
+        const int fg = ip + b;   // number of depth-n points below mu = searchsorted(side='left'), quantizer.py:74
+        const int il = clamp_index(fg, n, N, false), ir = clamp_index(fg, n, N, true);
+        const float npn = -sPen[n];
+        const float sl = score_exact(il == ip ? zp : point(n, il), mu, sg, rs, npn);
+        const float sr = score_exact(ir == ip ? zp : point(n, ir), mu, sg, rs, npn);
+        if (sl > bestL) { bestL = sl; nL = n; iL = il; }
+        if (sr > bestR) { bestR = sr; nR = n; iR = ir; }
+        ip = 2 * ip + b;
+    }
+    return bestR > bestL ? (nR << 24 | iR) : (nL << 24 | iL);
+}
+
+// The same search done by a whole warp for ONE coordinate (channel column sSc) whose walk ended at heap node Kd of depth
+// kd >= N: lane j scores candidate j of the reference's order left_0..left_N, right_1..right_N; the first maximum wins.
+// Every lane returns depth << 24 | index.  (A coordinate that the certificate rejects used to hold its warp, and with
+// it the tile's slot, for microseconds.)
+static __device__ __forceinline__ int reference_search_warp(const float *sSc, const float *sPen, float mu, float sg,
+                                                            int N, int Kd, int kd, int lane) {
+    const float rs = rcp_rn(sg);
+    const bool right = lane > N;
+    const int n = min(right ? lane - N : lane, N);
+    auto point = [&](int i) -> float { return sSc[((1 << n) + i) * VBQ_GROUP] * kWalkUnscale; };
+    const int ip = (Kd >> (kd - n)) - (1 << n);
+    const float zp = point(ip);
+    const int fg = ip + (mu > zp ? 1 : 0);
+    const int idx = clamp_index(fg, n, N, right);
+    float s = score_exact(idx == ip ? zp : point(idx), mu, sg, rs, -sPen[n]);
+    // sequential semantics: candidate 0 starts as the best whatever its score; a NaN never replaces anything
+    if (lane == 0) s = s != s ? CUDART_INF_F : s;
+    else if (s != s || lane > 2 * N) s = -CUDART_INF_F;
+    int who = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float so = __shfl_xor_sync(0xffffffffu, s, o);
+        const int wo = __shfl_xor_sync(0xffffffffu, who, o);
+        if (so > s || (so == s && wo < who)) { s = so; who = wo; }
+    }
+    const int wi = __shfl_sync(0xffffffffu, idx, who);
+    const int wn = who > N ? who - N : who;
+    return wn << 24 | wi;
+}
+
+// OUT: compiled output set (bit 0 zhat, 1 qidx, 2 level, 3 bits), at most two arrays, in ascending bit order.
+// NT > 0: max_bits_per_coord == NT at compile time; NT == 0: run time (<= kSmemDepth).
+// W = consumer warps; the CTA has W + 1 warps.
+template <bool TOTALS, int NT, int OUT, int W>
+__global__ void __launch_bounds__(32 * (W + 1), 1)
+    vbq_bisect_tma_kernel(const QArgs a, const __grid_constant__ TmaMaps maps, const UniformPen up) {
+    constexpr int U = 2, S = kSlots;
+    constexpr int kTileRows_ = kQuadRows * W;
+    constexpr int kBoxFloats = kTileRows_ * VBQ_GROUP;         // one array of one slot
+    constexpr int kSgOff = S * kBoxFloats;                     // sigma word = mu word + kSgOff
+    constexpr int kKeys = kSmemDepth + 1;
+    constexpr unsigned kDepthBits = 15u;
+    constexpr int kNOut = ((OUT & 1) ? 1 : 0) + ((OUT & 2) ? 1 : 0) + ((OUT & 4) ? 1 : 0) + ((OUT & 8) ? 1 : 0);
+    static_assert(kNOut <= 2, "a slot has room for two output arrays");
+    constexpr unsigned kTreeBytes = kWalkFloats * sizeof(float);
+
+    extern __shared__ __align__(1024) float smem[];
+    float *sSingle = smem;                                      // [2048][16]   heap order, all depths
+    float *sDbl = sSingle + kSingleRows * VBQ_GROUP;            // [256][2][16] depths 1..7, one copy per half-warp
+    float *sMu = sDbl + kDblRows * 2 * VBQ_GROUP;               // [S][4W][16]  mu boxes, later first outputs
+    float *sSg = sMu + S * kBoxFloats;                          // [S][4W][16]  sigma boxes, later second outputs
+    __shared__ double sRed[VBQ_TOTALS][kMaxThreads / 32];
+    __shared__ __align__(8) unsigned long long sBar[2 * S + 1];  // full[S], done[S], tree
+    __shared__ int4 sDesc[S];                                   // (valid rows of the tile or -1 = stop, range index, group, 0)
+    __shared__ float sPen[kKeys];
+    __shared__ bool sLast;
+
+    const int N = NT > 0 ? NT : a.N;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = lane & (VBQ_GROUP - 1);
+    const int par = lane >> 4;
+    const bool logvar = (a.flags & VBQ_FLAG_LOGVAR) != 0;
+    const int C = a.C;
+    const int rows = (int)a.rows;
+    const long long rows4 = (a.rows + 3) & ~3ll;
+    const long long vtotal = (rows4 + kSwitchRows) * a.n_groups - kSwitchRows;
+    const long long p0 = row_cut(vtotal * blockIdx.x / gridDim.x, rows4, a.n_groups);
+    const long long p1 = row_cut(vtotal * (blockIdx.x + 1) / gridDim.x, rows4, a.n_groups);
+    const unsigned bar_full = smem_u32(sBar), bar_done = smem_u32(sBar + S), bar_tree = smem_u32(sBar + 2 * S);
+
+#ifdef VBQ_TRACE
+    double *tr = a.partials + (size_t)kMaxGrid * VBQ_TOTALS * a.n_lambda + (size_t)blockIdx.x * 1024;
+    const int tw = warp == 0 ? 0 : (warp == W - 1 ? 1 : (warp == W / 2 ? 2 : -1));
+    if (threadIdx.x == 0) tr[0] = (double)gtime();
+#endif
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_done + 8 * s, W);   // one arrival per consumer warp
+        }
+        mbar_init(bar_tree, 1);
+        mbar_fence_init();
+    }
+    if (threadIdx.x < kKeys) sPen[threadIdx.x] = up.v[threadIdx.x];
+    __syncthreads();
+    pdl_wait();   // programmatic stream serialization: nothing global is touched before this point
+#ifdef VBQ_TRACE
+    if (threadIdx.x == 0) tr[1] = (double)gtime();
+#endif
+
+    // the next range of this CTA: rows [row_a, row_b) of group g (row_b a multiple of 4 or the padded end of the group)
+    auto next_range = [&](long long &pos, int &g, int &row_a, int &row_b) {
+        g = (int)(pos / rows4);
+        row_a = (int)(pos - (long long)g * rows4);
+        const long long end = min((long long)(g + 1) * rows4, p1);
+        row_b = (int)(end - (long long)g * rows4);
+        pos = end;
+    };
+
+    double acc_dist = 0.0;
+    int acc_level = 0;
+
+    if (warp == W) {
+        // =============================== producer warp (one lane) =======================================================
+        if (lane == 0) {
+            tma_prefetch_map(&maps.in[0]);
+            tma_prefetch_map(&maps.in[1]);
+            if (kNOut > 0) { tma_prefetch_map(&maps.out[0][0]); tma_prefetch_map(&maps.out[0][1]); }
+            if (kNOut > 1) { tma_prefetch_map(&maps.out[1][0]); tma_prefetch_map(&maps.out[1][1]); }
+            int t_issue = 0, t_retire = 0;     // CTA-wide tile counters: tile t lives in slot t % S
+            int ring_g[S], ring_row[S], ring_valid[S];
+            auto retire = [&](int t) {         // slot -> global once every consumer warp has arrived
+                const int s = t & (S - 1);
+                mbar_wait_sleepy(bar_done + 8 * s, (unsigned)(t / S) & 1u, 20000u);
+                TRACE_P(t, 1);
+                if (kNOut > 0) {
+                    // the consumers fenced their st.shared into the async proxy before arriving
+                    int g = 0, r0 = 0, valid = 0;
+#pragma unroll
+                    for (int j = 0; j < S; ++j)
+                        if (j == s) { g = ring_g[j]; r0 = ring_row[j]; valid = ring_valid[j]; }
+                    const unsigned base = smem_u32(sMu + s * kBoxFloats);
+                    if (valid == kTileRows_) {
+                        tma_store_3d(&maps.out[0][0], base, g * VBQ_GROUP, r0, 0);
+                        if (kNOut > 1) tma_store_3d(&maps.out[1][0], base + kSgOff * 4, g * VBQ_GROUP, r0, 0);
+                    } else {   // cut tile: only its first `valid` rows belong to this CTA
+                        for (int r = 0; r < valid; r += kQuadRows) {
+                            const unsigned o = (unsigned)r * VBQ_GROUP * 4;
+                            tma_store_3d(&maps.out[0][1], base + o, g * VBQ_GROUP, r0 + r, 0);
+                            if (kNOut > 1) tma_store_3d(&maps.out[1][1], base + kSgOff * 4 + o, g * VBQ_GROUP, r0 + r, 0);
+                        }
+                    }
+                    tma_store_commit();
+                    TRACE_P(t, 2);
+                    tma_store_wait_read<0>();   // the slot may be overwritten
+                    TRACE_P(t, 3);
+                }
+            };
+            auto load = [&](int t, int g, int r0, int valid, int range) {
+                const int s = t & (S - 1);
+                const unsigned base = smem_u32(sMu + s * kBoxFloats);
+                const unsigned bar = bar_full + 8 * s;
+#pragma unroll
+                for (int j = 0; j < S; ++j)
+                    if (j == s) { ring_g[j] = g; ring_row[j] = r0; ring_valid[j] = valid; }
+                sDesc[s] = make_int4(valid, range, g, 0);
+                TRACE_P(t, 0);
+                mbar_arrive_expect_tx(bar, 2 * kBoxFloats * 4);
+                tma_load_3d(base, &maps.in[0], g * VBQ_GROUP, r0, 0, bar);
+                tma_load_3d(base + kSgOff * 4, &maps.in[1], g * VBQ_GROUP, r0, 0, bar);
+            };
+            long long pos = p0;
+            int range = 0;
+            while (pos < p1) {
+                int g, row_a, row_b;
+                next_range(pos, g, row_a, row_b);
+                // every tile of the previous range has to be retired before its tree is overwritten
+                while (t_retire < t_issue) retire(t_retire++);
+                mbar_arrive_expect_tx(bar_tree, kTreeBytes);
+                bulk_load(smem_u32(sSingle), a.packed + (size_t)a.n_groups * kPadEntries * VBQ_GROUP + (size_t)g * kWalkFloats,
+                          kTreeBytes, bar_tree);
+                for (int r0 = row_a; r0 < row_b; r0 += kTileRows_) {
+                    if (t_issue - t_retire == S) retire(t_retire++);
+                    load(t_issue++, g, r0, min(kTileRows_, min(row_b, rows) - r0), range);
+                }
+                ++range;
+            }
+            while (t_retire < t_issue) retire(t_retire++);
+            // stop sign in the next slot (free: everything has been retired)
+            sDesc[t_issue & (S - 1)] = make_int4(-1, 0, 0, 0);
+            mbar_arrive(bar_full + 8 * (t_issue & (S - 1)));
+            if (kNOut > 0) tma_store_wait<0>();
+        }
+        __syncwarp();
+    } else {
+        // =============================== consumers =======================================================================
+        const unsigned kmask = a.keymask;
+        const unsigned t_sg = smem_u32(sSingle), t_db = smem_u32(sDbl);
+        // walk constants (see the header): floats whose bit patterns are (signed) byte addresses
+        const float A1 = __uint_as_float(t_db + 2 * 128 + 4 * lane);                      // node 2 of this lane's copy
+        const float Ec1 = __uint_as_float(0x80000000u | (t_db + 4 * lane));               // -(base of the double rows)
+        const float Ec2 = __uint_as_float(0x80000000u | (t_sg + 4 * col));                // -(base of the single rows)
+        const int esw = (int)(t_sg + 4 * col) - (int)(t_db + 4 * lane);
+        const float Esw = __uint_as_float(esw < 0 ? 0x80000000u | (unsigned)(-esw) : (unsigned)esw);
+        const float c128 = __uint_as_float(128u), c64 = __uint_as_float(64u);
+        const float *sSc = sSingle + col;
+        const int my_row = kQuadRows * warp;                     // first row of this warp's quad inside a tile
+        float *const lane_mu = sMu + (my_row + par) * VBQ_GROUP + col;   // coordinate u: + u * 32 floats; sigma: + kSgOff
+        float z0s = 0.0f;
+        int range = -1;
+        bool c_ok = false, group_full = false;
+
+        // one quad: U coordinates of this thread (quad rows par and 2 + par, channel col).  `mine` points at this
+        // thread's mu word of coordinate 0.  CHECK: some coordinates of the quad do not exist (`my_rows` rows do).
+        auto iteration = [&](auto check_tag, auto lv_tag, float *mine, const int my_rows) {
+            constexpr bool CHECK = decltype(check_tag)::value;
+            constexpr bool LV = decltype(lv_tag)::value;
+            float2 nmu2, r2;
+            bool ok[U];
+            {
+                float mu[U], sg[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    ok[u] = !CHECK || (c_ok && par + 2 * u < my_rows);
+                    mu[u] = mine[u * 2 * VBQ_GROUP];
+                    float s = mine[kSgOff + u * 2 * VBQ_GROUP];
+                    if (CHECK && !ok[u]) { mu[u] = 0.0f; s = LV ? 0.0f : 1.0f; }
+                    if (LV) s = sqrtf(expf(s));
+                    sg[u] = s;
+                }
+                nmu2 = __fmul2_rn(make_float2(mu[0], mu[1]), make_float2(-kWalkScale, -kWalkScale));
+                r2 = __fmul2_rn(make_float2(rcp_approx(sg[0]), rcp_approx(sg[1])),
+                                make_float2(0.70710678f * kWalkUnscale, 0.70710678f * kWalkUnscale));
+            }
+            unsigned key[U][kKeys];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int n = 0; n < kKeys; ++n) key[u][n] = (0x7fffffffu & ~kDepthBits) | (unsigned)n;
+            float2 G;   // bit patterns = shared-memory byte addresses of the path nodes of the next depth
+            {
+                const float2 d = __fadd2_rn(make_float2(z0s, z0s), nmu2);
+                const float2 st = make_float2(mul_sat(d.x, -1.7014118e38f), mul_sat(d.y, -1.7014118e38f));
+                G = __ffma2_rn(st, make_float2(c128, c128), make_float2(A1, A1));
+                const float2 t = __fmul2_rn(d, r2);
+                const float2 A = __ffma2_rn(t, t, make_float2(up.v[0], up.v[0]));
+                key[0][0] = make_key<0>(A.x, kmask);
+                key[1][0] = make_key<0>(A.y, kmask);
+            }
+            auto depth = [&](auto n_tag) {
+                constexpr int n = decltype(n_tag)::value;
+                const float2 z = make_float2(lds_pure(__float_as_uint(G.x)), lds_pure(__float_as_uint(G.y)));
+                const float2 d = __fadd2_rn(z, nmu2);
+                if (n < kSmemDepth && (NT > 0 ? n < NT : true)) {   // the address of the next path node
+                    float2 GL;
+                    if (n < kDblDepth) GL = __ffma2_rn(G, make_float2(2.0f, 2.0f), make_float2(Ec1, Ec1));
+                    else if (n == kDblDepth) GL = __fadd2_rn(G, make_float2(Esw, Esw));
+                    else GL = __ffma2_rn(G, make_float2(2.0f, 2.0f), make_float2(Ec2, Ec2));
+                    const float2 st = make_float2(mul_sat(d.x, -1.7014118e38f), mul_sat(d.y, -1.7014118e38f));
+                    const float stride = n < kDblDepth ? c128 : c64;
+                    G = __ffma2_rn(st, make_float2(stride, stride), GL);
+                }
+                const float2 t = __fmul2_rn(d, r2);
+                const float2 A = __ffma2_rn(t, t, make_float2(up.v[n], up.v[n]));
+                key[0][n] = make_key<n>(A.x, kmask);
+                key[1][n] = make_key<n>(A.y, kmask);
+            };
+            int m_done = 0;   // deepest depth visited: G addresses its path node ... one step further if m_done < N
+#define VBQ_DEPTH(n_)                                                                                          \
+    if constexpr (n_ <= kSmemDepth) {                                                                          \
+        if (NT > 0 ? n_ <= NT : n_ <= N) {                                                                     \
+            depth(std::integral_constant<int, n_>{});                                                          \
+            m_done = n_;                                                                                       \
+        }                                                                                                      \
+    }
+            VBQ_DEPTH(1) VBQ_DEPTH(2) VBQ_DEPTH(3) VBQ_DEPTH(4) VBQ_DEPTH(5)
+            VBQ_DEPTH(6) VBQ_DEPTH(7) VBQ_DEPTH(8) VBQ_DEPTH(9) VBQ_DEPTH(10)
+#undef VBQ_DEPTH
+            static_assert(kSmemDepth == 10, "the depth macro list above covers depths 1..10");
+            // G addresses the node of depth kd: kd = m_done + 1 if the walk stopped above the last tree level (N <
+            // kSmemDepth: it then points at one of the repeated ancestors), else the depth-10 path node itself
+            const int kd = m_done < kSmemDepth ? m_done + 1 : kSmemDepth;
+
+            int wn[U], wP[U], Kd[U];
+            unsigned gap[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const unsigned *k_ = key[u];
+                unsigned m = k_[0];
+#pragma unroll
+                for (int n = 1; n + 1 < kKeys; n += 2) m = __vimin3_u32(m, k_[n], k_[n + 1]);
+                if (kKeys % 2 == 0) m = min(m, k_[kKeys - 1]);
+                const unsigned nm = ~m;
+                unsigned g0 = 0xffffffffu, g1 = 0xffffffffu;
+#pragma unroll
+                for (int n = 0; n < kKeys; n += 2) g0 = __viaddmin_u32(k_[n], nm, g0);
+#pragma unroll
+                for (int n = 1; n < kKeys; n += 2) g1 = __viaddmin_u32(k_[n], nm, g1);
+                gap[u] = min(g0, g1);
+                wn[u] = (int)(m & kDepthBits);
+                // heap index of the node G addresses, then of its ancestor at the winning depth
+                const unsigned gb = __float_as_uint(u ? G.y : G.x);
+                Kd[u] = kd <= kDblDepth ? (int)((gb - (t_db + 4 * lane)) >> 7) : (int)((gb - (t_sg + 4 * col)) >> 6);
+                wP[u] = Kd[u] >> (kd - wn[u]);
+            }
+            if (__any_sync(0xffffffffu, min(gap[0], gap[1]) <= kKeyGuard)) {
+                // rare (a few coordinates in 10^5): the coordinates that are not certified redo the literal search on
+                // the reloaded inputs — the whole warp for one coordinate when they are few, else every lane for itself
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    float m_ = mine[u * 2 * VBQ_GROUP], s_ = mine[kSgOff + u * 2 * VBQ_GROUP];
+                    if (CHECK && !ok[u]) { m_ = 0.0f; s_ = LV ? 0.0f : 1.0f; }
+                    if (LV) s_ = sqrtf(expf(s_));
+                    unsigned todo = __ballot_sync(0xffffffffu, gap[u] <= kKeyGuard);
+                    if (__popc(todo) <= 6) {
+                        while (todo) {
+                            const int L = __ffs(todo) - 1;
+                            todo &= todo - 1;
+                            const int r = reference_search_warp(sSingle + (L & (VBQ_GROUP - 1)), sPen,
+                                                                __shfl_sync(0xffffffffu, m_, L), __shfl_sync(0xffffffffu, s_, L),
+                                                                N, __shfl_sync(0xffffffffu, Kd[u], L), kd, lane);
+                            if (lane == L) {
+                                wn[u] = r >> 24;
+                                wP[u] = (1 << wn[u]) + (r & 0xffffff);
+                            }
+                        }
+                    } else if (gap[u] <= kKeyGuard) {
+                        const int r = reference_search_walk(sSc, sPen, m_, s_, N);
+                        wn[u] = r >> 24;
+                        wP[u] = (1 << wn[u]) + (r & 0xffffff);
+                    }
+                }
+            }
+            float dist[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int n = wn[u], Pn = wP[u];
+                dist[u] = 0.0f;
+                // sorted index q = (2i+1) 2^(N-n) - 1 with i = Pn - 2^n
+                const int q = ((2 * Pn + 1) << (N - n)) - (2 << N) - 1;
+                float zh = 0.0f;   // scaled by 2^24
+                if (TOTALS || (OUT & 1)) zh = lds_pure((unsigned)imad(Pn, kRowStrideBytes, (int)(t_sg + 4 * col)));
+                // the outputs replace this thread's own inputs in the slot (first output array in the mu box)
+                int slot_word = 0;
+                if (OUT & 1) { mine[slot_word * kSgOff + u * 2 * VBQ_GROUP] = zh * kWalkUnscale; ++slot_word; }
+                if (OUT & 2) { reinterpret_cast<int *>(mine)[slot_word * kSgOff + u * 2 * VBQ_GROUP] = q; ++slot_word; }
+                if (OUT & 4) { reinterpret_cast<int *>(mine)[slot_word * kSgOff + u * 2 * VBQ_GROUP] = n; ++slot_word; }
+                if (OUT & 8) { mine[slot_word * kSgOff + u * 2 * VBQ_GROUP] = (float)n; ++slot_word; }
+                if (TOTALS && ok[u]) {
+                    const float t = (zh + (u ? nmu2.y : nmu2.x)) * (u ? r2.y : r2.x);
+                    acc_level += n;
+                    dist[u] = t * t;
+                }
+            }
+            if (TOTALS) acc_dist += (double)(dist[0] + dist[1]);   // float32 per quad, float64 across quads, fixed order
+        };
+
+        auto run = [&](auto lv_tag) {
+            for (int t = 0;; ++t) {
+                const int s = t & (S - 1);
+                TRACE_C(t, 0);
+                mbar_wait_sleepy(bar_full + 8 * s, (unsigned)(t / S) & 1u, 20000u);
+                TRACE_C(t, 1);
+                const int4 d = sDesc[s];
+                if (d.x < 0) break;
+                if (d.y != range) {   // a new range: its tree, first code point and channel
+                    range = d.y;
+                    mbar_wait(bar_tree, (unsigned)range & 1u);
+                    z0s = sSc[VBQ_GROUP];
+                    c_ok = d.z * VBQ_GROUP + col < C;
+                    group_full = d.z * VBQ_GROUP + VBQ_GROUP <= C;
+                }
+                const int my_rows = d.x - my_row;   // rows of this warp's quad that belong to the tile
+                float *mine = lane_mu + s * kBoxFloats;
+                if (my_rows >= kQuadRows && group_full) iteration(std::false_type{}, lv_tag, mine, kQuadRows);
+                else if (my_rows > 0) iteration(std::true_type{}, lv_tag, mine, my_rows);
+                if (kNOut > 0) fence_proxy_async();   // this thread's st.shared -> visible to the TMA store
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_done + 8 * s);
+                TRACE_C(t, 2);
+            }
+        };
+        if (logvar) run(std::true_type{});
+        else run(std::false_type{});
+    }
+
+#ifdef VBQ_TRACE
+    if (threadIdx.x == 0) tr[2] = (double)gtime();
+    if (threadIdx.x == 32 * W) tr[3] = (double)gtime();
+#endif
+    if (TOTALS) {
+        double v[VBQ_TOTALS] = {(double)acc_level, (double)acc_level, 0.0, acc_dist};
+        finish_totals<32 * (W + 1)>(a, 0, v, sRed, &sLast);
+    }
+#ifdef VBQ_TRACE
+    if (threadIdx.x == 0) tr[4] = (double)gtime();
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
+            qr != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+int vbq_make_tensor_map(CUtensorMap *out, const void *base, int C, long long rows, long long planes,
+                        long long plane_stride, int box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return vbq_fail(VBQ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)rows, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)C * 4u, (cuuint64_t)plane_stride * 4u};
+    const cuuint32_t box[3] = {VBQ_GROUP, (cuuint32_t)box_rows, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return vbq_fail(VBQ_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return VBQ_OK;
+}
+
+static_assert(vbq_walk_tree_floats(1) == kWalkFloats, "layout of the walk tree (tree.cuh, quantize.cu)");
+
+template <bool TOTALS, int NT, int OUT, int W>
+static int launch_tma(const QArgs &a0, const void *out0, const void *out1, int dev, int sms, cudaStream_t st) {
+    constexpr int kTile = kQuadRows * W;
+    const long long rows4 = (a0.rows + 3) & ~3ll;
+    long long gx = rows4 / kQuadRows * a0.n_groups;   // quads
+    gx = gx < sms ? gx : sms;
+    if (gx > kMaxGrid) gx = kMaxGrid;
+    if (gx < 1) gx = 1;
+    auto kern = vbq_bisect_tma_kernel<TOTALS, NT, OUT, W>;
+    VBQ_ENSURE_MAX_SMEM(kern, dev);
+    const size_t smem = ((size_t)kWalkFloats + (size_t)kSlots * 2 * kTile * VBQ_GROUP) * sizeof(float);
+    const long long plane = a0.rows * (long long)a0.C;
+    for (int lam = 0; lam < a0.n_lambda; ++lam) {   // one launch per lambda (several lambdas normally take the sweep kernel)
+        QArgs a = a0;
+        const size_t lo = (size_t)lam * a0.lam_stride;
+        const char *o0 = out0 ? (const char *)out0 + lo * 4 : nullptr, *o1 = out1 ? (const char *)out1 + lo * 4 : nullptr;
+        if (a.totals) a.totals = a0.totals + (size_t)lam * VBQ_TOTALS;
+        a.n_lambda = 1;
+        TmaMaps maps;
+        RETURN_IF(vbq_make_tensor_map(&maps.in[0], a.mu, a.C, a.rows, 1, plane, kTile));
+        RETURN_IF(vbq_make_tensor_map(&maps.in[1], a.sigma, a.C, a.rows, 1, plane, kTile));
+        for (int k = 0; k < 2; ++k) {   // unused output maps repeat an input map so that the parameter block is initialised
+            const int br = k == 0 ? kTile : kQuadRows;
+            RETURN_IF(vbq_make_tensor_map(&maps.out[0][k], o0 ? o0 : (const void *)a.mu, a.C, a.rows, 1, plane, br));
+            RETURN_IF(vbq_make_tensor_map(&maps.out[1][k], o1 ? o1 : (const void *)a.mu, a.C, a.rows, 1, plane, br));
+        }
+        UniformPen up;
+        const float *hp = a0.h_pen + (size_t)lam * (a0.N + 1);
+        for (int n = 0; n <= kSmemDepth; ++n) up.v[n] = n <= a.N ? hp[n] : HUGE_VALF;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((int)gx);
+        cfg.blockDim = dim3(32 * (W + 1));
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        static const bool pdl = !getenv("VBQ_NO_PDL");
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl ? 1 : 0;
+        CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a, maps, up));
+    }
+    return VBQ_OK;
+}
+
+constexpr int kConsumerWarps = 31;
+
+template <bool TOTALS, int NT>
+static int launch_tma3(const QArgs &a, int dev, int sms, cudaStream_t st) {
+    constexpr int W = kConsumerWarps;
+#ifdef VBQ_DEV_ONE   // development builds: only the benchmark's variant (fast compile, small SASS listing)
+    if constexpr (TOTALS && NT == 10) {
+        if ((a.outm & 15u) == (2u | 8u)) return launch_tma<true, 10, 2 | 8, W>(a, a.qidx, a.bits, dev, sms, st);
+    }
+    return -1;
+#else
+    switch (a.outm & 15u) {
+        case 2u | 8u: return launch_tma<TOTALS, NT, 2 | 8, W>(a, a.qidx, a.bits, dev, sms, st);
+        case 1u | 4u: return launch_tma<TOTALS, NT, 1 | 4, W>(a, a.zhat, a.level, dev, sms, st);
+        case 1u: return launch_tma<TOTALS, NT, 1, W>(a, a.zhat, nullptr, dev, sms, st);
+        case 2u: return launch_tma<TOTALS, NT, 2, W>(a, a.qidx, nullptr, dev, sms, st);
+        case 0u:
+            if constexpr (TOTALS) return launch_tma<TOTALS, NT, 0, W>(a, nullptr, nullptr, dev, sms, st);
+            return -1;
+        default: return -1;
+    }
+#endif
+}
+
+// raw code lengths that do not depend on the channel, available on the host (vbq_quantize_hp) and non-decreasing in the
+// bit depth; max_bits_per_coord <= 10; C % 4 == 0 and 16-byte aligned arrays (TMA); at most two outputs of the compiled
+// sets.  Returns -1 if not applicable (the caller falls back to vbq_bisect_kernel, the cp.async formulation).
+int vbq_launch_quantize_tma(const QArgs &a, int dev, int sms, cudaStream_t st) {
+    if (a.len || a.em || a.N > kSmemDepth || a.C % 4 != 0 || !a.h_pen || a.pen_channels != 1) return -1;
+    uintptr_t al = (uintptr_t)a.mu | (uintptr_t)a.sigma | (uintptr_t)a.zhat | (uintptr_t)a.qidx | (uintptr_t)a.level |
+                   (uintptr_t)a.bits | (uintptr_t)a.packed;
+    if (al & 15) return -1;
+    if (a.rows * (long long)a.C >= (1ll << 31)) return -1;
+    for (int l = 0; l < a.n_lambda; ++l) {   // the certified ranking needs 0 <= pen_0 <= pen_1 <= ... (false for NaN)
+        float prev = 0.0f;
+        for (int n = 0; n <= a.N; ++n) {
+            const float p = a.h_pen[(size_t)l * (a.N + 1) + n];
+            if (!(p >= prev)) return -1;
+            prev = p;
+        }
+    }
+    if (a.N == kSmemDepth) return a.totals ? launch_tma3<true, kSmemDepth>(a, dev, sms, st) : launch_tma3<false, kSmemDepth>(a, dev, sms, st);
+    return a.totals ? launch_tma3<true, 0>(a, dev, sms, st) : launch_tma3<false, 0>(a, dev, sms, st);
+}

@@ -26,6 +26,7 @@ FLAG_REFERENCE_WALK = _lib.FLAG_REFERENCE_WALK
 FLAG_RESERVE_SM = _lib.FLAG_RESERVE_SM
 FLAG_BRACKET_WALK = _lib.FLAG_BRACKET_WALK
 FLAG_WORKSPACE_ZEROED = _lib.FLAG_WORKSPACE_ZEROED
+FLAG_NO_TMA = _lib.FLAG_NO_TMA
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -45,6 +46,24 @@ def _need_cuda(name, t, dtype, ndim=None):
         raise ValueError("vbq_b200: `%s` must be contiguous" % name)
     if ndim is not None and t.dim() != ndim:
         raise ValueError("vbq_b200: `%s` must be %d-D, got shape %s" % (name, ndim, tuple(t.shape)))
+
+
+def with_host_copy(penalty_np, device):
+    """Device tensor of a host-made penalty table that remembers its host original (float32, C-contiguous).  The
+    search kernels take channel-independent penalties of a single lambda as launch constants when the host copy is
+    available (vbq_quantize_hp); the device tensor alone works too."""
+    import numpy as np
+    host = np.ascontiguousarray(penalty_np, dtype=np.float32)
+    t = torch.from_numpy(host).to(device)
+    t._vbq_host = host
+    return t
+
+
+def _host_penalty_ptr(penalty):
+    host = getattr(penalty, "_vbq_host", None)
+    if host is None or tuple(host.shape) != tuple(penalty.shape):
+        return None
+    return host.ctypes.data
 
 
 def search_flags(lambs, flags=0):
@@ -107,11 +126,11 @@ def quantize_into(mu, sigma, table, packed, penalty, length, entropy_model, max_
         if workspace is None:
             raise ValueError("vbq_b200: totals need a workspace (see quantize_workspace)")
         ws_bytes = workspace.numel() * workspace.element_size()
-    st = lib.vbq_quantize(_ptr(mu), _ptr(sigma), rows, C, _ptr(table), _ptr(packed), max_bits,
-                          _ptr(penalty), _ptr(length), n_lambda, pen_channels, _ptr(entropy_model),
-                          _ptr(zhat), _ptr(qidx), _ptr(level), _ptr(bits), _ptr(em_bits), _ptr(totals),
-                          _ptr(workspace), ws_bytes, flags, _stream(mu.device))
-    _lib.check(st, "vbq_quantize")
+    st = lib.vbq_quantize_hp(_ptr(mu), _ptr(sigma), rows, C, _ptr(table), _ptr(packed), max_bits,
+                             _ptr(penalty), _host_penalty_ptr(penalty), _ptr(length), n_lambda, pen_channels,
+                             _ptr(entropy_model), _ptr(zhat), _ptr(qidx), _ptr(level), _ptr(bits), _ptr(em_bits),
+                             _ptr(totals), _ptr(workspace), ws_bytes, flags, _stream(mu.device))
+    _lib.check(st, "vbq_quantize_hp")
 
 
 def quantize_workspace(n_lambda, device):
@@ -139,8 +158,9 @@ class QuantizePlan:
         quantize_into(*self._args, **self._kw)     # validates everything once (and sets the kernels' attributes)
         rows, C = mu.shape
         n_lambda, pen_channels, _ = penalty.shape
-        self._fn = _lib.load().vbq_quantize
+        self._fn = _lib.load().vbq_quantize_hp
         self._cargs = (_ptr(mu), _ptr(sigma), rows, C, _ptr(table), _ptr(packed), max_bits, _ptr(penalty),
+                       _host_penalty_ptr(penalty),
                        _ptr(length), n_lambda, pen_channels, _ptr(entropy_model), _ptr(zhat), _ptr(qidx), _ptr(level),
                        _ptr(bits), _ptr(em_bits), _ptr(totals), _ptr(ws),
                        0 if ws is None else ws.numel() * ws.element_size(), self._kw["flags"])
@@ -155,7 +175,7 @@ class QuantizePlan:
     def _call(self):
         st = self._fn(*self._cargs, _stream(self._device))
         if st != _lib.OK:
-            _lib.check(st, "vbq_quantize")
+            _lib.check(st, "vbq_quantize_hp")
 
     def run(self):
         if self._graph is not None:

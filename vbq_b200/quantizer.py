@@ -93,7 +93,7 @@ class ChannelwisePriorCDFQuantizer:
             Ls = [raw + np.asarray(self.raw_code_length_entropy_models[l], dtype=np.float32).T for l in lambs]
             pen = np.stack([l32 * Ll for l32, Ll in zip(lam32, Ls)]).transpose(0, 2, 1)   # (Lambda, C, N+1)
             length = torch.from_numpy(np.ascontiguousarray(np.stack(Ls).transpose(0, 2, 1))).to(self.device)
-        pen = torch.from_numpy(np.ascontiguousarray(pen, dtype=np.float32)).to(self.device)
+        pen = ops.with_host_copy(pen, self.device)
         self._cache[key] = (pen, length)
         return pen, length
 
