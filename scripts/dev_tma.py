@@ -107,7 +107,7 @@ def main():
                         same = all(torch.equal(r_[k], n_[k]) for k in r_)
                         relt = ((tn - tr).abs() / tr.abs().clamp_min(1e-300)).max().item()
                         n2_, tn2 = run_once(qq, m, s, pen_, l2, f, outs, N)
-                        if not same or relt > 1e-9 or (pen_ is p2 and not torch.equal(tn, tn2)):
+                        if not same or relt > 2e-7 or (pen_ is p2 and not torch.equal(tn, tn2)):
                             print("MISMATCH rows=%d C=%d N=%d lambs=%s outs=%s flags=%d same=%s totals rel %.2e repro %s" %
                                   (rows, C, N, lambs, outs, f, same, relt, torch.equal(tn, tn2)))
                             raise SystemExit(1)

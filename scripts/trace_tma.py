@@ -26,19 +26,28 @@ for k, w in enumerate(W):
 w = W[2]
 dur = (w[:, 2] - w[:, 1]) / 1e3
 print("consumer duration per CTA: min %.2f max %.2f mean %.2f; slowest CTAs %s" % (dur.min(), dur.max(), dur.mean(), np.argsort(dur)[-8:]))
-for cta in (0, 70, int(np.argmax(dur))):
-    t0 = w[cta, 1]
-    P = w[cta, 8:264].reshape(64, 4)
-    Cc = w[cta, 264:264 + 3 * 64 * 3].reshape(3, 64, 3)
-    nt = int((P[:, 0] > 0).sum())
-    print("CTA %d: %d tiles, consumer time %.2f us" % (cta, nt, dur[cta]))
-    for wi, name in enumerate(("warp 0", "warp W-1", "warp W/2")):
-        c = Cc[wi][:nt]
-        waits = c[:, 1] - c[:, 0]
-        work = c[:, 2] - c[:, 1]
-        print("   %s: wait per tile mean %.0f ns (max %.0f), work per tile mean %.0f ns; wait share %.1f%%" % (
-            name, waits.mean(), waits.max(), work.mean(), 100 * waits.sum() / (waits.sum() + work.sum())))
-    for t in range(min(nt, 14)):
-        print("   tile %2d: load issued %.2f | full seen w0 %.2f wL %.2f | end w0 %.2f wL %.2f wM %.2f | done seen %.2f stored %.2f slot read %.2f" % (
-            t, (P[t, 0] - t0) / 1e3, (Cc[0, t, 1] - t0) / 1e3, (Cc[1, t, 1] - t0) / 1e3, (Cc[0, t, 2] - t0) / 1e3,
-            (Cc[1, t, 2] - t0) / 1e3, (Cc[2, t, 2] - t0) / 1e3, (P[t, 1] - t0) / 1e3, (P[t, 2] - t0) / 1e3, (P[t, 3] - t0) / 1e3))
+
+# per-CTA: ranges (replicating row_cut of quantize_tma.cu) and tiles vs duration
+SW, rows4, ng, grid = 448, (bench.ROWS + 3) // 4 * 4, (bench.C + 15) // 16, 148
+def row_cut(v):
+    vg = rows4 + SW
+    g = min((v + SW) // vg, ng)
+    o = v + SW - g * vg
+    return g * rows4 + (((o - SW) // 4 * 4) if o > SW else 0)
+vtotal = (rows4 + SW) * ng - SW
+info = []
+for b in range(grid):
+    p0, p1 = row_cut(vtotal * b // grid), row_cut(vtotal * (b + 1) // grid)
+    nr = (p1 - 1) // rows4 - p0 // rows4 + 1
+    P = w[b, 8:264].reshape(64, 4)
+    first_full = (P[0, 1] - w[b, 1]) / 1e3
+    info.append((b, nr, p1 - p0, dur[b], (w[b, 3] - w[b, 2]) / 1e3, (w[b, 4] - w[b, 3]) / 1e3))
+info = np.array(info)
+for nr in (1, 2):
+    m = info[:, 1] == nr
+    if m.any():
+        print("CTAs with %d range(s): %d, rows %.0f, consumer time mean %.2f min %.2f max %.2f; producer tail %.2f; exit tail %.2f" % (
+            nr, m.sum(), info[m, 2].mean(), info[m, 3].mean(), info[m, 3].min(), info[m, 3].max(), info[m, 4].mean(), info[m, 5].mean()))
+order = np.argsort(info[:, 3])
+print("fastest:", [(int(info[i, 0]), int(info[i, 1]), round(info[i, 3], 1)) for i in order[:10]])
+print("slowest:", [(int(info[i, 0]), int(info[i, 1]), round(info[i, 3], 1)) for i in order[-10:]])

@@ -36,14 +36,16 @@
 #include "tma.cuh"
 
 constexpr int kQuadRows = 4;
+constexpr int kTmaRows = 128;                // rows of a tile = one TMA box per array
 constexpr int kSlots = 4;                  // tiles in flight per CTA
 constexpr int kDblDepth = 7;               // bit depths 1..kDblDepth also exist as one copy per half-warp
 constexpr int kSingleRows = 1 << (kSmemDepth + 1);               // heap index K = 1 .. 2047, row 0 unused
 constexpr int kDblRows = 1 << (kDblDepth + 1);                   // K = 2 .. 255, rows 0 and 1 unused
+constexpr int kTmaSmemBytes = 229376 + 512;   // walk tree + kSlots x (mu box + sigma box) + barriers, descriptors, ticket counter, penalties
 constexpr int kWalkFloats = kSingleRows * VBQ_GROUP + kDblRows * 2 * VBQ_GROUP;   // 40960 floats = 160 KB per group
 constexpr float kWalkScale = 16777216.0f;                        // 2^24
 constexpr float kWalkUnscale = 1.0f / 16777216.0f;
-constexpr long long kSwitchRows = 320;     // a second range (new tree) costs a CTA about as much as this many rows
+constexpr long long kSwitchRows = 448;     // a second range (new tree) costs a CTA about as much as this many rows
 
 struct TmaMaps {
     CUtensorMap in[2];       // mu, sigma: box of 4W rows
@@ -70,11 +72,36 @@ __device__ __forceinline__ unsigned long long gtime() {
     return t;
 }
 #define TRACE_P(tile, k) do { if ((tile) < 64) tr[8 + (tile) * 4 + (k)] = (double)gtime(); } while (0)
-#define TRACE_C(tile, k) do { if (lane == 0 && (tile) < 64 && tw >= 0) tr[264 + (tw * 64 + (tile)) * 3 + (k)] = (double)gtime(); } while (0)
+#define TRACE_C(tile, k) do {} while (0)
 #else
 #define TRACE_P(tile, k) do {} while (0)
 #define TRACE_C(tile, k) do {} while (0)
 #endif
+
+__device__ __forceinline__ void sts_u32(unsigned addr, unsigned v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts_v4(unsigned addr, int x, int y, int z, int w) {
+    asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ unsigned lds_u32i(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ int4 lds_v4(unsigned addr) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+// lane 0 takes the next ticket of the CTA-wide counter (atom.inc with wrap bound 2^31-1 = a plain increment: for
+// atom.add ptxas emits its 17-instruction warp-aggregation sequence around this single-lane atomic); the other lanes get
+// the value by a shuffle from lane 0 later
+__device__ __forceinline__ int claim_ticket(unsigned counter_addr, int lane) {
+    int j = 0;
+    if (lane == 0) asm volatile("atom.shared.inc.u32 %0, [%1], 0x7fffffff;" : "=r"(j) : "r"(counter_addr) : "memory");
+    return j;
+}
 
 __device__ __forceinline__ float mul_sat(float a, float b) {
     float r;
@@ -137,30 +164,42 @@ static __device__ __forceinline__ int reference_search_warp(const float *sSc, co
 
 // OUT: compiled output set (bit 0 zhat, 1 qidx, 2 level, 3 bits), at most two arrays, in ascending bit order.
 // NT > 0: max_bits_per_coord == NT at compile time; NT == 0: run time (<= kSmemDepth).
-// W = consumer warps; the CTA has W + 1 warps.
-template <bool TOTALS, int NT, int OUT, int W>
+// W = consumer warps (the CTA has W + 1 warps); P = coordinate pairs per thread: a warp iteration ("unit") covers
+// 4P consecutive rows x 16 channels, lane = (row parity, channel), coordinates at rows parity + 2u, u < 2P.
+template <bool TOTALS, int NT, int OUT, int W, int P>
 __global__ void __launch_bounds__(32 * (W + 1), 1)
     vbq_bisect_tma_kernel(const QArgs a, const __grid_constant__ TmaMaps maps, const UniformPen up) {
-    constexpr int U = 2, S = kSlots;
-    constexpr int kTileRows_ = kQuadRows * W;
-    constexpr int kBoxFloats = kTileRows_ * VBQ_GROUP;         // one array of one slot
+    constexpr int U = 2 * P, S = kSlots;
+    constexpr int kUnitRows = kQuadRows * P;
+    constexpr int kUnits = kTmaRows / kUnitRows;               // units (tickets) per tile
+    constexpr int kLogUnits = P == 1 ? 5 : (P == 2 ? 4 : 3);
+    constexpr int kUnitFloats = kUnitRows * VBQ_GROUP;
+    constexpr int kBoxFloats = kTmaRows * VBQ_GROUP;           // one array of one slot
     constexpr int kSgOff = S * kBoxFloats;                     // sigma word = mu word + kSgOff
     constexpr int kKeys = kSmemDepth + 1;
     constexpr unsigned kDepthBits = 15u;
     constexpr int kNOut = ((OUT & 1) ? 1 : 0) + ((OUT & 2) ? 1 : 0) + ((OUT & 4) ? 1 : 0) + ((OUT & 8) ? 1 : 0);
     static_assert(kNOut <= 2, "a slot has room for two output arrays");
+    static_assert((P == 1 || P == 2 || P == 4) && S == 4 && kTmaRows == 128, "ticket bit fields");
     constexpr unsigned kTreeBytes = kWalkFloats * sizeof(float);
 
+    // dynamic shared memory, byte offsets (everything the main loop touches sits at a constant offset from ONE base
+    // register; left to itself the compiler re-derives the window address of every __shared__ object in every iteration)
+    constexpr unsigned kOffDbl = kSingleRows * VBQ_GROUP * 4;             // [256][2][16] depths 1..7, one copy per half-warp
+    constexpr unsigned kOffMu = kOffDbl + kDblRows * 2 * VBQ_GROUP * 4;   // [S][128][16] mu boxes, later first outputs
+    constexpr unsigned kOffSg = kOffMu + kSgOff * 4;                      // [S][128][16] sigma boxes, later second outputs
+    constexpr unsigned kOffBar = kOffSg + kSgOff * 4;                     // full[S], done[S], tree: 8 bytes each
+    constexpr unsigned kOffDesc = kOffBar + 128;                          // int4[S]: (valid rows, range index, group, 0)
+    constexpr unsigned kOffNext = kOffDesc + 16 * S;                      // next unclaimed ticket; + 4: number of tickets
+    constexpr unsigned kOffPen = kOffNext + 16;                           // float[kKeys]
+    static_assert(kOffPen + 4 * kKeys <= kTmaSmemBytes, "shared-memory layout");
     extern __shared__ __align__(1024) float smem[];
     float *sSingle = smem;                                      // [2048][16]   heap order, all depths
-    float *sDbl = sSingle + kSingleRows * VBQ_GROUP;            // [256][2][16] depths 1..7, one copy per half-warp
-    float *sMu = sDbl + kDblRows * 2 * VBQ_GROUP;               // [S][4W][16]  mu boxes, later first outputs
-    float *sSg = sMu + S * kBoxFloats;                          // [S][4W][16]  sigma boxes, later second outputs
+    float *sPen = smem + kOffPen / 4;
     __shared__ double sRed[VBQ_TOTALS][kMaxThreads / 32];
-    __shared__ __align__(8) unsigned long long sBar[2 * S + 1];  // full[S], done[S], tree
-    __shared__ int4 sDesc[S];                                   // (valid rows of the tile or -1 = stop, range index, group, 0)
-    __shared__ float sPen[kKeys];
     __shared__ bool sLast;
+    unsigned sm0 = smem_u32(smem);
+    asm volatile("" : "+r"(sm0));   // opaque: keep it in a register
 
     const int N = NT > 0 ? NT : a.N;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -173,27 +212,7 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
     const long long vtotal = (rows4 + kSwitchRows) * a.n_groups - kSwitchRows;
     const long long p0 = row_cut(vtotal * blockIdx.x / gridDim.x, rows4, a.n_groups);
     const long long p1 = row_cut(vtotal * (blockIdx.x + 1) / gridDim.x, rows4, a.n_groups);
-    const unsigned bar_full = smem_u32(sBar), bar_done = smem_u32(sBar + S), bar_tree = smem_u32(sBar + 2 * S);
-
-#ifdef VBQ_TRACE
-    double *tr = a.partials + (size_t)kMaxGrid * VBQ_TOTALS * a.n_lambda + (size_t)blockIdx.x * 1024;
-    const int tw = warp == 0 ? 0 : (warp == W - 1 ? 1 : (warp == W / 2 ? 2 : -1));
-    if (threadIdx.x == 0) tr[0] = (double)gtime();
-#endif
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < S; ++s) {
-            mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_done + 8 * s, W);   // one arrival per consumer warp
-        }
-        mbar_init(bar_tree, 1);
-        mbar_fence_init();
-    }
-    if (threadIdx.x < kKeys) sPen[threadIdx.x] = up.v[threadIdx.x];
-    __syncthreads();
-    pdl_wait();   // programmatic stream serialization: nothing global is touched before this point
-#ifdef VBQ_TRACE
-    if (threadIdx.x == 0) tr[1] = (double)gtime();
-#endif
+    const unsigned bar_full = sm0 + kOffBar, bar_done = bar_full + 8 * S, bar_tree = bar_full + 16 * S;
 
     // the next range of this CTA: rows [row_a, row_b) of group g (row_b a multiple of 4 or the padded end of the group)
     auto next_range = [&](long long &pos, int &g, int &row_a, int &row_b) {
@@ -204,7 +223,34 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
         pos = end;
     };
 
-    double acc_dist = 0.0;
+#ifdef VBQ_TRACE
+    double *tr = a.partials + (size_t)kMaxGrid * VBQ_TOTALS * a.n_lambda + (size_t)blockIdx.x * 1024;
+    if (threadIdx.x == 0) tr[0] = (double)gtime();
+#endif
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_done + 8 * s, kUnits);   // one arrival per unit of the tile
+        }
+        mbar_init(bar_tree, 1);
+        mbar_fence_init();
+        int n_tiles = 0;
+        for (long long pos = p0; pos < p1;) {
+            int g, row_a, row_b;
+            next_range(pos, g, row_a, row_b);
+            n_tiles += (row_b - row_a + kTmaRows - 1) / kTmaRows;
+        }
+        sts_u32(sm0 + kOffNext, 0u);
+        sts_u32(sm0 + kOffNext + 4, (unsigned)(n_tiles * kUnits));
+    }
+    if (threadIdx.x < kKeys) sPen[threadIdx.x] = up.v[threadIdx.x];
+    __syncthreads();
+    pdl_wait();   // programmatic stream serialization: nothing global is touched before this point
+#ifdef VBQ_TRACE
+    if (threadIdx.x == 0) tr[1] = (double)gtime();
+#endif
+
+    unsigned long long acc_dist = 0;   // sum of the distortion terms in units of 2^-24: integer, so the order does not matter
     int acc_level = 0;
 
     if (warp == W) {
@@ -216,7 +262,7 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
             if (kNOut > 1) { tma_prefetch_map(&maps.out[1][0]); tma_prefetch_map(&maps.out[1][1]); }
             int t_issue = 0, t_retire = 0;     // CTA-wide tile counters: tile t lives in slot t % S
             int ring_g[S], ring_row[S], ring_valid[S];
-            auto retire = [&](int t) {         // slot -> global once every consumer warp has arrived
+            auto retire = [&](int t) {         // slot -> global once every unit of the tile has been computed
                 const int s = t & (S - 1);
                 mbar_wait_sleepy(bar_done + 8 * s, (unsigned)(t / S) & 1u, 20000u);
                 TRACE_P(t, 1);
@@ -226,8 +272,8 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
 #pragma unroll
                     for (int j = 0; j < S; ++j)
                         if (j == s) { g = ring_g[j]; r0 = ring_row[j]; valid = ring_valid[j]; }
-                    const unsigned base = smem_u32(sMu + s * kBoxFloats);
-                    if (valid == kTileRows_) {
+                    const unsigned base = sm0 + kOffMu + s * (kBoxFloats * 4);
+                    if (valid == kTmaRows) {
                         tma_store_3d(&maps.out[0][0], base, g * VBQ_GROUP, r0, 0);
                         if (kNOut > 1) tma_store_3d(&maps.out[1][0], base + kSgOff * 4, g * VBQ_GROUP, r0, 0);
                     } else {   // cut tile: only its first `valid` rows belong to this CTA
@@ -245,12 +291,12 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
             };
             auto load = [&](int t, int g, int r0, int valid, int range) {
                 const int s = t & (S - 1);
-                const unsigned base = smem_u32(sMu + s * kBoxFloats);
+                const unsigned base = sm0 + kOffMu + s * (kBoxFloats * 4);
                 const unsigned bar = bar_full + 8 * s;
 #pragma unroll
                 for (int j = 0; j < S; ++j)
                     if (j == s) { ring_g[j] = g; ring_row[j] = r0; ring_valid[j] = valid; }
-                sDesc[s] = make_int4(valid, range, g, 0);
+                sts_v4(sm0 + kOffDesc + 16 * s, valid, range, g, 0);
                 TRACE_P(t, 0);
                 mbar_arrive_expect_tx(bar, 2 * kBoxFloats * 4);
                 tma_load_3d(base, &maps.in[0], g * VBQ_GROUP, r0, 0, bar);
@@ -264,25 +310,23 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
                 // every tile of the previous range has to be retired before its tree is overwritten
                 while (t_retire < t_issue) retire(t_retire++);
                 mbar_arrive_expect_tx(bar_tree, kTreeBytes);
-                bulk_load(smem_u32(sSingle), a.packed + (size_t)a.n_groups * kPadEntries * VBQ_GROUP + (size_t)g * kWalkFloats,
+                bulk_load(sm0, a.packed + (size_t)a.n_groups * kPadEntries * VBQ_GROUP + (size_t)g * kWalkFloats,
                           kTreeBytes, bar_tree);
-                for (int r0 = row_a; r0 < row_b; r0 += kTileRows_) {
+                for (int r0 = row_a; r0 < row_b; r0 += kTmaRows) {
                     if (t_issue - t_retire == S) retire(t_retire++);
-                    load(t_issue++, g, r0, min(kTileRows_, min(row_b, rows) - r0), range);
+                    load(t_issue++, g, r0, min(kTmaRows, min(row_b, rows) - r0), range);
                 }
                 ++range;
             }
             while (t_retire < t_issue) retire(t_retire++);
-            // stop sign in the next slot (free: everything has been retired)
-            sDesc[t_issue & (S - 1)] = make_int4(-1, 0, 0, 0);
-            mbar_arrive(bar_full + 8 * (t_issue & (S - 1)));
-            if (kNOut > 0) tma_store_wait<0>();
+            // every store has READ its slot (retire waits for that), which is all the CTA owes the copies before it
+            // exits; their global writes complete before the grid does
         }
         __syncwarp();
     } else {
         // =============================== consumers =======================================================================
         const unsigned kmask = a.keymask;
-        const unsigned t_sg = smem_u32(sSingle), t_db = smem_u32(sDbl);
+        const unsigned t_sg = sm0, t_db = sm0 + kOffDbl;
         // walk constants (see the header): floats whose bit patterns are (signed) byte addresses
         const float A1 = __uint_as_float(t_db + 2 * 128 + 4 * lane);                      // node 2 of this lane's copy
         const float Ec1 = __uint_as_float(0x80000000u | (t_db + 4 * lane));               // -(base of the double rows)
@@ -291,68 +335,77 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
         const float Esw = __uint_as_float(esw < 0 ? 0x80000000u | (unsigned)(-esw) : (unsigned)esw);
         const float c128 = __uint_as_float(128u), c64 = __uint_as_float(64u);
         const float *sSc = sSingle + col;
-        const int my_row = kQuadRows * warp;                     // first row of this warp's quad inside a tile
-        float *const lane_mu = sMu + (my_row + par) * VBQ_GROUP + col;   // coordinate u: + u * 32 floats; sigma: + kSgOff
+        const unsigned lane_mu = sm0 + kOffMu + 4 * lane;   // coordinate u of a unit: + u * 128 bytes; sigma: + 4 kSgOff
         float z0s = 0.0f;
-        int range = -1;
+        int range = -1, cur_tile = -1, valid = 0;
         bool c_ok = false, group_full = false;
 
-        // one quad: U coordinates of this thread (quad rows par and 2 + par, channel col).  `mine` points at this
-        // thread's mu word of coordinate 0.  CHECK: some coordinates of the quad do not exist (`my_rows` rows do).
-        auto iteration = [&](auto check_tag, auto lv_tag, float *mine, const int my_rows) {
+        // one unit: U coordinates of this thread (unit rows par + 2u, channel col).  `mine` points at this thread's mu
+        // word of coordinate 0.  CHECK: some coordinates of the unit do not exist (`my_rows` rows do).
+        auto iteration = [&](auto check_tag, auto lv_tag, const unsigned mine, const int my_rows) {
             constexpr bool CHECK = decltype(check_tag)::value;
             constexpr bool LV = decltype(lv_tag)::value;
-            float2 nmu2, r2;
+            float2 nmu2[P], r2[P];
             bool ok[U];
             {
                 float mu[U], sg[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     ok[u] = !CHECK || (c_ok && par + 2 * u < my_rows);
-                    mu[u] = mine[u * 2 * VBQ_GROUP];
-                    float s = mine[kSgOff + u * 2 * VBQ_GROUP];
+                    mu[u] = lds_u32(mine + u * 128);
+                    float s = lds_u32(mine + 4 * kSgOff + u * 128);
                     if (CHECK && !ok[u]) { mu[u] = 0.0f; s = LV ? 0.0f : 1.0f; }
                     if (LV) s = sqrtf(expf(s));
                     sg[u] = s;
                 }
-                nmu2 = __fmul2_rn(make_float2(mu[0], mu[1]), make_float2(-kWalkScale, -kWalkScale));
-                r2 = __fmul2_rn(make_float2(rcp_approx(sg[0]), rcp_approx(sg[1])),
-                                make_float2(0.70710678f * kWalkUnscale, 0.70710678f * kWalkUnscale));
+#pragma unroll
+                for (int k = 0; k < P; ++k) {
+                    nmu2[k] = __fmul2_rn(make_float2(mu[2 * k], mu[2 * k + 1]), make_float2(-kWalkScale, -kWalkScale));
+                    r2[k] = __fmul2_rn(make_float2(rcp_approx(sg[2 * k]), rcp_approx(sg[2 * k + 1])),
+                                       make_float2(0.70710678f * kWalkUnscale, 0.70710678f * kWalkUnscale));
+                }
             }
             unsigned key[U][kKeys];
 #pragma unroll
             for (int u = 0; u < U; ++u)
 #pragma unroll
                 for (int n = 0; n < kKeys; ++n) key[u][n] = (0x7fffffffu & ~kDepthBits) | (unsigned)n;
-            float2 G;   // bit patterns = shared-memory byte addresses of the path nodes of the next depth
-            {
-                const float2 d = __fadd2_rn(make_float2(z0s, z0s), nmu2);
+            float2 G[P];   // bit patterns = shared-memory byte addresses of the path nodes of the next depth
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                const float2 d = __fadd2_rn(make_float2(z0s, z0s), nmu2[k]);
                 const float2 st = make_float2(mul_sat(d.x, -1.7014118e38f), mul_sat(d.y, -1.7014118e38f));
-                G = __ffma2_rn(st, make_float2(c128, c128), make_float2(A1, A1));
-                const float2 t = __fmul2_rn(d, r2);
+                G[k] = __ffma2_rn(st, make_float2(c128, c128), make_float2(A1, A1));
+                const float2 t = __fmul2_rn(d, r2[k]);
                 const float2 A = __ffma2_rn(t, t, make_float2(up.v[0], up.v[0]));
-                key[0][0] = make_key<0>(A.x, kmask);
-                key[1][0] = make_key<0>(A.y, kmask);
+                key[2 * k][0] = make_key<0>(A.x, kmask);
+                key[2 * k + 1][0] = make_key<0>(A.y, kmask);
             }
             auto depth = [&](auto n_tag) {
                 constexpr int n = decltype(n_tag)::value;
-                const float2 z = make_float2(lds_pure(__float_as_uint(G.x)), lds_pure(__float_as_uint(G.y)));
-                const float2 d = __fadd2_rn(z, nmu2);
-                if (n < kSmemDepth && (NT > 0 ? n < NT : true)) {   // the address of the next path node
-                    float2 GL;
-                    if (n < kDblDepth) GL = __ffma2_rn(G, make_float2(2.0f, 2.0f), make_float2(Ec1, Ec1));
-                    else if (n == kDblDepth) GL = __fadd2_rn(G, make_float2(Esw, Esw));
-                    else GL = __ffma2_rn(G, make_float2(2.0f, 2.0f), make_float2(Ec2, Ec2));
-                    const float2 st = make_float2(mul_sat(d.x, -1.7014118e38f), mul_sat(d.y, -1.7014118e38f));
-                    const float stride = n < kDblDepth ? c128 : c64;
-                    G = __ffma2_rn(st, make_float2(stride, stride), GL);
+                float2 z[P];
+#pragma unroll
+                for (int k = 0; k < P; ++k)
+                    z[k] = make_float2(lds_pure(__float_as_uint(G[k].x)), lds_pure(__float_as_uint(G[k].y)));
+#pragma unroll
+                for (int k = 0; k < P; ++k) {
+                    const float2 d = __fadd2_rn(z[k], nmu2[k]);
+                    if (n < kSmemDepth && (NT > 0 ? n < NT : true)) {   // the address of the next path node
+                        float2 GL;
+                        if (n < kDblDepth) GL = __ffma2_rn(G[k], make_float2(2.0f, 2.0f), make_float2(Ec1, Ec1));
+                        else if (n == kDblDepth) GL = __fadd2_rn(G[k], make_float2(Esw, Esw));
+                        else GL = __ffma2_rn(G[k], make_float2(2.0f, 2.0f), make_float2(Ec2, Ec2));
+                        const float2 st = make_float2(mul_sat(d.x, -1.7014118e38f), mul_sat(d.y, -1.7014118e38f));
+                        const float stride = n < kDblDepth ? c128 : c64;
+                        G[k] = __ffma2_rn(st, make_float2(stride, stride), GL);
+                    }
+                    const float2 t = __fmul2_rn(d, r2[k]);
+                    const float2 A = __ffma2_rn(t, t, make_float2(up.v[n], up.v[n]));
+                    key[2 * k][n] = make_key<n>(A.x, kmask);
+                    key[2 * k + 1][n] = make_key<n>(A.y, kmask);
                 }
-                const float2 t = __fmul2_rn(d, r2);
-                const float2 A = __ffma2_rn(t, t, make_float2(up.v[n], up.v[n]));
-                key[0][n] = make_key<n>(A.x, kmask);
-                key[1][n] = make_key<n>(A.y, kmask);
             };
-            int m_done = 0;   // deepest depth visited: G addresses its path node ... one step further if m_done < N
+            int m_done = 0;   // deepest depth visited
 #define VBQ_DEPTH(n_)                                                                                          \
     if constexpr (n_ <= kSmemDepth) {                                                                          \
         if (NT > 0 ? n_ <= NT : n_ <= N) {                                                                     \
@@ -369,7 +422,7 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
             const int kd = m_done < kSmemDepth ? m_done + 1 : kSmemDepth;
 
             int wn[U], wP[U], Kd[U];
-            unsigned gap[U];
+            unsigned gap[U], gap_min = 0xffffffffu;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const unsigned *k_ = key[u];
@@ -384,18 +437,19 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
 #pragma unroll
                 for (int n = 1; n < kKeys; n += 2) g1 = __viaddmin_u32(k_[n], nm, g1);
                 gap[u] = min(g0, g1);
+                gap_min = min(gap_min, gap[u]);
                 wn[u] = (int)(m & kDepthBits);
                 // heap index of the node G addresses, then of its ancestor at the winning depth
-                const unsigned gb = __float_as_uint(u ? G.y : G.x);
+                const unsigned gb = __float_as_uint(u & 1 ? G[u / 2].y : G[u / 2].x);
                 Kd[u] = kd <= kDblDepth ? (int)((gb - (t_db + 4 * lane)) >> 7) : (int)((gb - (t_sg + 4 * col)) >> 6);
                 wP[u] = Kd[u] >> (kd - wn[u]);
             }
-            if (__any_sync(0xffffffffu, min(gap[0], gap[1]) <= kKeyGuard)) {
+            if (__any_sync(0xffffffffu, gap_min <= kKeyGuard)) {
                 // rare (a few coordinates in 10^5): the coordinates that are not certified redo the literal search on
                 // the reloaded inputs — the whole warp for one coordinate when they are few, else every lane for itself
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    float m_ = mine[u * 2 * VBQ_GROUP], s_ = mine[kSgOff + u * 2 * VBQ_GROUP];
+                    float m_ = lds_u32(mine + u * 128), s_ = lds_u32(mine + 4 * kSgOff + u * 128);
                     if (CHECK && !ok[u]) { m_ = 0.0f; s_ = LV ? 0.0f : 1.0f; }
                     if (LV) s_ = sqrtf(expf(s_));
                     unsigned todo = __ballot_sync(0xffffffffu, gap[u] <= kKeyGuard);
@@ -418,53 +472,61 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
                     }
                 }
             }
-            float dist[U];
+            float dsum = 0.0f;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int n = wn[u], Pn = wP[u];
-                dist[u] = 0.0f;
                 // sorted index q = (2i+1) 2^(N-n) - 1 with i = Pn - 2^n
                 const int q = ((2 * Pn + 1) << (N - n)) - (2 << N) - 1;
                 float zh = 0.0f;   // scaled by 2^24
                 if (TOTALS || (OUT & 1)) zh = lds_pure((unsigned)imad(Pn, kRowStrideBytes, (int)(t_sg + 4 * col)));
                 // the outputs replace this thread's own inputs in the slot (first output array in the mu box)
                 int slot_word = 0;
-                if (OUT & 1) { mine[slot_word * kSgOff + u * 2 * VBQ_GROUP] = zh * kWalkUnscale; ++slot_word; }
-                if (OUT & 2) { reinterpret_cast<int *>(mine)[slot_word * kSgOff + u * 2 * VBQ_GROUP] = q; ++slot_word; }
-                if (OUT & 4) { reinterpret_cast<int *>(mine)[slot_word * kSgOff + u * 2 * VBQ_GROUP] = n; ++slot_word; }
-                if (OUT & 8) { mine[slot_word * kSgOff + u * 2 * VBQ_GROUP] = (float)n; ++slot_word; }
+                if (OUT & 1) { sts_u32(mine + slot_word * 4 * kSgOff + u * 128, __float_as_uint(zh * kWalkUnscale)); ++slot_word; }
+                if (OUT & 2) { sts_u32(mine + slot_word * 4 * kSgOff + u * 128, (unsigned)q); ++slot_word; }
+                if (OUT & 4) { sts_u32(mine + slot_word * 4 * kSgOff + u * 128, (unsigned)n); ++slot_word; }
+                if (OUT & 8) { sts_u32(mine + slot_word * 4 * kSgOff + u * 128, __float_as_uint((float)n)); ++slot_word; }
                 if (TOTALS && ok[u]) {
-                    const float t = (zh + (u ? nmu2.y : nmu2.x)) * (u ? r2.y : r2.x);
+                    const float t = (zh + (u & 1 ? nmu2[u / 2].y : nmu2[u / 2].x)) * (u & 1 ? r2[u / 2].y : r2[u / 2].x);
                     acc_level += n;
-                    dist[u] = t * t;
+                    dsum = __fmaf_rn(t, t, dsum);
                 }
             }
-            if (TOTALS) acc_dist += (double)(dist[0] + dist[1]);   // float32 per quad, float64 across quads, fixed order
+            // float32 within the thread's coordinates of the unit, then an exact integer sum (saturating conversion):
+            // whichever warp computes whichever unit, the total is the same
+            if (TOTALS) acc_dist += __float2ull_rn(dsum * 16777216.0f);
         };
 
         auto run = [&](auto lv_tag) {
-            for (int t = 0;; ++t) {
-                const int s = t & (S - 1);
-                TRACE_C(t, 0);
-                mbar_wait_sleepy(bar_full + 8 * s, (unsigned)(t / S) & 1u, 20000u);
-                TRACE_C(t, 1);
-                const int4 d = sDesc[s];
-                if (d.x < 0) break;
-                if (d.y != range) {   // a new range: its tree, first code point and channel
-                    range = d.y;
-                    mbar_wait(bar_tree, (unsigned)range & 1u);
-                    z0s = sSc[VBQ_GROUP];
-                    c_ok = d.z * VBQ_GROUP + col < C;
-                    group_full = d.z * VBQ_GROUP + VBQ_GROUP <= C;
+            const int n_tickets = (int)lds_u32i(sm0 + kOffNext + 4);
+            int kk = __shfl_sync(0xffffffffu, claim_ticket(sm0 + kOffNext, lane), 0);
+            while (kk < n_tickets) {
+                // the next ticket one iteration ahead; its value is read at the end of this iteration, so the atomic's
+                // latency never stalls the warp
+                const int nxt_raw = claim_ticket(sm0 + kOffNext, lane);
+                const int tile = kk >> kLogUnits;
+                const unsigned sb = ((unsigned)tile & (S - 1)) * 8u;
+                if (tile != cur_tile) {
+                    cur_tile = tile;
+                    mbar_wait_sleepy(bar_full + sb, ((unsigned)tile >> 2) & 1u, 20000u);
+                    const int4 d = lds_v4(sm0 + kOffDesc + 2 * sb);
+                    valid = d.x;
+                    if (d.y != range) {   // a new range: its tree, first code point and channel
+                        range = d.y;
+                        mbar_wait(bar_tree, (unsigned)range & 1u);
+                        z0s = lds_u32(sm0 + 4 * (VBQ_GROUP + col));
+                        c_ok = d.z * VBQ_GROUP + col < C;
+                        group_full = d.z * VBQ_GROUP + VBQ_GROUP <= C;
+                    }
                 }
-                const int my_rows = d.x - my_row;   // rows of this warp's quad that belong to the tile
-                float *mine = lane_mu + s * kBoxFloats;
-                if (my_rows >= kQuadRows && group_full) iteration(std::false_type{}, lv_tag, mine, kQuadRows);
+                const int my_rows = valid - (kk & (kUnits - 1)) * kUnitRows;   // rows of this unit that belong to the tile
+                const unsigned mine = lane_mu + (kk & (S * kUnits - 1)) * (kUnitFloats * 4);
+                if (my_rows >= kUnitRows && group_full) iteration(std::false_type{}, lv_tag, mine, kUnitRows);
                 else if (my_rows > 0) iteration(std::true_type{}, lv_tag, mine, my_rows);
                 if (kNOut > 0) fence_proxy_async();   // this thread's st.shared -> visible to the TMA store
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_done + 8 * s);
-                TRACE_C(t, 2);
+                if (lane == 0) mbar_arrive(bar_done + sb);
+                kk = __shfl_sync(0xffffffffu, nxt_raw, 0);
             }
         };
         if (logvar) run(std::true_type{});
@@ -476,8 +538,24 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
     if (threadIdx.x == 32 * W) tr[3] = (double)gtime();
 #endif
     if (TOTALS) {
-        double v[VBQ_TOTALS] = {(double)acc_level, (double)acc_level, 0.0, acc_dist};
-        finish_totals<32 * (W + 1)>(a, 0, v, sRed, &sLast);
+        // integer sums inside the CTA (exact), then the float64 partials of the CTAs in a fixed order (finish_totals)
+        unsigned long long *sQ = reinterpret_cast<unsigned long long *>(&sRed[0][0]);
+        int *sL = reinterpret_cast<int *>(&sRed[1][0]);
+        acc_level = __reduce_add_sync(0xffffffffu, acc_level);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc_dist += __shfl_xor_sync(0xffffffffu, acc_dist, o);
+        if (lane == 0) { sQ[warp] = acc_dist; sL[warp] = acc_level; }
+        __syncthreads();
+        if (warp == 0) {
+            acc_dist = lane <= W ? sQ[lane] : 0ull;
+            acc_level = lane <= W ? sL[lane] : 0;
+            acc_level = __reduce_add_sync(0xffffffffu, acc_level);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc_dist += __shfl_xor_sync(0xffffffffu, acc_dist, o);
+        }
+        // acc_dist < 2^53 converts exactly; the sums over the CTAs are then sums of multiples of 2^-24
+        const double v[VBQ_TOTALS] = {(double)acc_level, (double)acc_level, 0.0, (double)acc_dist * (1.0 / 16777216.0)};
+        publish_totals<32 * (W + 1)>(a, 0, v, sRed, &sLast);
     }
 #ifdef VBQ_TRACE
     if (threadIdx.x == 0) tr[4] = (double)gtime();
@@ -520,17 +598,18 @@ int vbq_make_tensor_map(CUtensorMap *out, const void *base, int C, long long row
 
 static_assert(vbq_walk_tree_floats(1) == kWalkFloats, "layout of the walk tree (tree.cuh, quantize.cu)");
 
-template <bool TOTALS, int NT, int OUT, int W>
+template <bool TOTALS, int NT, int OUT, int W, int P>
 static int launch_tma(const QArgs &a0, const void *out0, const void *out1, int dev, int sms, cudaStream_t st) {
-    constexpr int kTile = kQuadRows * W;
+    constexpr int kTile = kTmaRows;
     const long long rows4 = (a0.rows + 3) & ~3ll;
     long long gx = rows4 / kQuadRows * a0.n_groups;   // quads
     gx = gx < sms ? gx : sms;
     if (gx > kMaxGrid) gx = kMaxGrid;
     if (gx < 1) gx = 1;
-    auto kern = vbq_bisect_tma_kernel<TOTALS, NT, OUT, W>;
+    auto kern = vbq_bisect_tma_kernel<TOTALS, NT, OUT, W, P>;
     VBQ_ENSURE_MAX_SMEM(kern, dev);
-    const size_t smem = ((size_t)kWalkFloats + (size_t)kSlots * 2 * kTile * VBQ_GROUP) * sizeof(float);
+    static_assert(((size_t)kWalkFloats + (size_t)kSlots * 2 * kTile * VBQ_GROUP) * sizeof(float) + 512 == kTmaSmemBytes, "slots");
+    const size_t smem = kTmaSmemBytes;
     const long long plane = a0.rows * (long long)a0.C;
     for (int lam = 0; lam < a0.n_lambda; ++lam) {   // one launch per lambda (several lambdas normally take the sweep kernel)
         QArgs a = a0;
@@ -565,24 +644,39 @@ static int launch_tma(const QArgs &a0, const void *out0, const void *out1, int d
     return VBQ_OK;
 }
 
-constexpr int kConsumerWarps = 31;
+constexpr int kConsumerWarps = 19, kPairs = 2;   // measured: 31x1 46.7, 23x1 46.1, 15x2 45.0, 17x2 44.9, 19x2 43.4, 21x2 45.1 (spills), 11x4 48.5 us per Kodak step
 
 template <bool TOTALS, int NT>
 static int launch_tma3(const QArgs &a, int dev, int sms, cudaStream_t st) {
-    constexpr int W = kConsumerWarps;
+    constexpr int W = kConsumerWarps, P = kPairs;
+#ifdef VBQ_DEV_VARIANTS   // development: geometry variants of the benchmark's kernel, chosen by VBQ_TMA_VARIANT
+    if constexpr (TOTALS && NT == 10) {
+        const char *v = getenv("VBQ_TMA_VARIANT");
+        const int vi = v ? atoi(v) : 0;
+        if ((a.outm & 15u) == (2u | 8u) && vi > 0) {
+            if (vi == 1) return launch_tma<true, 10, 2 | 8, 17, 2>(a, a.qidx, a.bits, dev, sms, st);
+            if (vi == 2) return launch_tma<true, 10, 2 | 8, 21, 2>(a, a.qidx, a.bits, dev, sms, st);
+            if (vi == 3) return launch_tma<true, 10, 2 | 8, 19, 2>(a, a.qidx, a.bits, dev, sms, st);
+            if (vi == 4) return launch_tma<true, 10, 2 | 8, 23, 2>(a, a.qidx, a.bits, dev, sms, st);
+            if (vi == 5) return launch_tma<true, 10, 2 | 8, 11, 4>(a, a.qidx, a.bits, dev, sms, st);
+            if (vi == 6) return launch_tma<true, 10, 2 | 8, 13, 4>(a, a.qidx, a.bits, dev, sms, st);
+            if (vi == 7) return launch_tma<true, 10, 2 | 8, 9, 4>(a, a.qidx, a.bits, dev, sms, st);
+        }
+    }
+#endif
 #ifdef VBQ_DEV_ONE   // development builds: only the benchmark's variant (fast compile, small SASS listing)
     if constexpr (TOTALS && NT == 10) {
-        if ((a.outm & 15u) == (2u | 8u)) return launch_tma<true, 10, 2 | 8, W>(a, a.qidx, a.bits, dev, sms, st);
+        if ((a.outm & 15u) == (2u | 8u)) return launch_tma<true, 10, 2 | 8, W, P>(a, a.qidx, a.bits, dev, sms, st);
     }
     return -1;
 #else
     switch (a.outm & 15u) {
-        case 2u | 8u: return launch_tma<TOTALS, NT, 2 | 8, W>(a, a.qidx, a.bits, dev, sms, st);
-        case 1u | 4u: return launch_tma<TOTALS, NT, 1 | 4, W>(a, a.zhat, a.level, dev, sms, st);
-        case 1u: return launch_tma<TOTALS, NT, 1, W>(a, a.zhat, nullptr, dev, sms, st);
-        case 2u: return launch_tma<TOTALS, NT, 2, W>(a, a.qidx, nullptr, dev, sms, st);
+        case 2u | 8u: return launch_tma<TOTALS, NT, 2 | 8, W, P>(a, a.qidx, a.bits, dev, sms, st);
+        case 1u | 4u: return launch_tma<TOTALS, NT, 1 | 4, W, P>(a, a.zhat, a.level, dev, sms, st);
+        case 1u: return launch_tma<TOTALS, NT, 1, W, P>(a, a.zhat, nullptr, dev, sms, st);
+        case 2u: return launch_tma<TOTALS, NT, 2, W, P>(a, a.qidx, nullptr, dev, sms, st);
         case 0u:
-            if constexpr (TOTALS) return launch_tma<TOTALS, NT, 0, W>(a, nullptr, nullptr, dev, sms, st);
+            if constexpr (TOTALS) return launch_tma<TOTALS, NT, 0, W, P>(a, nullptr, nullptr, dev, sms, st);
             return -1;
         default: return -1;
     }
