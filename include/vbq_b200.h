@@ -61,6 +61,10 @@ enum {
                                          ticket counters) are zero: true after a cudaMemset at allocation and after every
                                          completed call, which leaves them zero again.  Saves the per-call memset node
                                          (about 5 us of stream time on a B200). */
+#define VBQ_FLAG_TABLE_STABLE 1024u     /* the caller vouches that d_packed was completely written before the PREVIOUS operation
+                                         on `stream` was enqueued (e.g. it synchronized after vbq_pack_code_points): the search
+                                         kernel then fetches its code points while the stream's previous kernel still drains
+                                         (programmatic dependent launch) instead of after it */
 #define VBQ_FLAG_NO_TMA 512u           /* single lambda: stage the latents with per-warp cp.async (vbq_bisect_kernel) instead
                                          of the TMA pipeline (vbq_bisect_tma_kernel); same results, for comparison */
 #define VBQ_FLAG_BRACKET_WALK 128u     /* single lambda: use the nearer-bracket-end walk (strict mode) even where the

@@ -144,7 +144,7 @@ extern "C" int vbq_quantize_hp(const float *d_mu, const float *d_sigma, long lon
     RETURN_IF(vbq_check_depth(N));
     if (flags & ~(VBQ_FLAG_LOGVAR | VBQ_FLAG_NO_PRUNE | VBQ_FLAG_FAST | VBQ_FLAG_ACCUMULATE_TOTALS | VBQ_FLAG_NO_SWEEP |
                   VBQ_FLAG_REFERENCE_WALK | VBQ_FLAG_RESERVE_SM | VBQ_FLAG_BRACKET_WALK | VBQ_FLAG_WORKSPACE_ZEROED |
-                  VBQ_FLAG_NO_TMA))
+                  VBQ_FLAG_NO_TMA | VBQ_FLAG_TABLE_STABLE))
         return vbq_fail(VBQ_ERR_BAD_FLAGS, "vbq_quantize: unknown flag bits 0x%x", flags);
     if (!d_table || !d_packed || !d_penalty || (rows > 0 && (!d_mu || !d_sigma)))
         return vbq_fail(VBQ_ERR_NULL_POINTER, "vbq_quantize: null input pointer");
@@ -161,7 +161,7 @@ extern "C" int vbq_quantize_hp(const float *d_mu, const float *d_sigma, long lon
     a.pen = d_penalty; a.h_pen = h_penalty; a.len = d_length; a.n_lambda = n_lambda; a.pen_channels = pen_channels;
     a.em = d_entropy_model;
     a.zhat = d_zhat; a.qidx = d_qidx; a.level = d_level; a.bits = d_bits; a.em_bits = d_em_bits;
-    a.totals = d_totals; a.partials = nullptr; a.ticket = nullptr;
+    a.totals = d_totals; a.partials = nullptr; a.ticket = nullptr; a.queue = nullptr;
     a.flags = flags;
     a.one = 1;
     a.two = 2;
@@ -179,8 +179,9 @@ extern "C" int vbq_quantize_hp(const float *d_mu, const float *d_sigma, long lon
             return vbq_fail(VBQ_ERR_MISALIGNED, "vbq_quantize: workspace not 256-byte aligned");
         a.ticket = (unsigned *)d_workspace;
         a.partials = (double *)((char *)d_workspace + ticket_bytes(n_lambda));
-        if (!(flags & VBQ_FLAG_WORKSPACE_ZEROED))
-            CUDA_TRY(cudaMemsetAsync(a.ticket, 0, (size_t)n_lambda * sizeof(unsigned), st));
+        // one lambda: the rest of the first 256-byte block holds the tile queues of vbq_bisect_tma_kernel (zero between calls)
+        if (n_lambda == 1 && a.n_groups <= 62) a.queue = a.ticket + 1;
+        if (!(flags & VBQ_FLAG_WORKSPACE_ZEROED)) CUDA_TRY(cudaMemsetAsync(a.ticket, 0, ticket_bytes(n_lambda), st));
     }
     if (rows == 0) {
         if (d_totals) CUDA_TRY(cudaMemsetAsync(d_totals, 0, (size_t)n_lambda * VBQ_TOTALS * sizeof(double), st));

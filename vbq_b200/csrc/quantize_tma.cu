@@ -103,6 +103,18 @@ __device__ __forceinline__ int claim_ticket(unsigned counter_addr, int lane) {
     return j;
 }
 
+// the dynamic tile queues: one counter per group in global memory
+__device__ __forceinline__ unsigned queue_claim(unsigned *q) {
+    unsigned v;
+    asm volatile("atom.add.relaxed.gpu.global.u32 %0, [%1], 1;" : "=r"(v) : "l"(q) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned queue_peek(const unsigned *q) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(q) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ float mul_sat(float a, float b) {
     float r;
     asm("mul.rn.sat.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
@@ -234,18 +246,19 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
         }
         mbar_init(bar_tree, 1);
         mbar_fence_init();
-        int n_tiles = 0;
-        for (long long pos = p0; pos < p1;) {
-            int g, row_a, row_b;
-            next_range(pos, g, row_a, row_b);
-            n_tiles += (row_b - row_a + kTmaRows - 1) / kTmaRows;
-        }
         sts_u32(sm0 + kOffNext, 0u);
-        sts_u32(sm0 + kOffNext + 4, (unsigned)(n_tiles * kUnits));
     }
     if (threadIdx.x < kKeys) sPen[threadIdx.x] = up.v[threadIdx.x];
     __syncthreads();
-    pdl_wait();   // programmatic stream serialization: nothing global is touched before this point
+    // programmatic stream serialization: nothing global is touched before pdl_wait() — except the code points of the
+    // first range when the caller vouches that they were complete before the previous kernel of the stream started
+    const int home_g = a.queue ? (int)((long long)blockIdx.x * a.n_groups / gridDim.x) : (int)min(p0 / rows4, (long long)a.n_groups - 1);
+    const bool early_tree = (a.flags & VBQ_FLAG_TABLE_STABLE) != 0;
+    if (early_tree && threadIdx.x == 32 * W) {
+        mbar_arrive_expect_tx(bar_tree, kTreeBytes);
+        bulk_load(sm0, a.packed + (size_t)a.n_groups * kPadEntries * VBQ_GROUP + (size_t)home_g * kWalkFloats, kTreeBytes, bar_tree);
+    }
+    pdl_wait();
 #ifdef VBQ_TRACE
     if (threadIdx.x == 0) tr[1] = (double)gtime();
 #endif
@@ -302,25 +315,70 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
                 tma_load_3d(base, &maps.in[0], g * VBQ_GROUP, r0, 0, bar);
                 tma_load_3d(base + kSgOff * 4, &maps.in[1], g * VBQ_GROUP, r0, 0, bar);
             };
-            long long pos = p0;
-            int range = 0;
-            while (pos < p1) {
-                int g, row_a, row_b;
-                next_range(pos, g, row_a, row_b);
-                // every tile of the previous range has to be retired before its tree is overwritten
-                while (t_retire < t_issue) retire(t_retire++);
-                mbar_arrive_expect_tx(bar_tree, kTreeBytes);
-                bulk_load(sm0, a.packed + (size_t)a.n_groups * kPadEntries * VBQ_GROUP + (size_t)g * kWalkFloats,
-                          kTreeBytes, bar_tree);
-                for (int r0 = row_a; r0 < row_b; r0 += kTmaRows) {
-                    if (t_issue - t_retire == S) retire(t_retire++);
-                    load(t_issue++, g, r0, min(kTmaRows, min(row_b, rows) - r0), range);
+            int n_trees = early_tree ? 1 : 0;   // tree loads so far; the consumers wait for phase (range index) & 1
+            int cur_g = early_tree ? home_g : -1;   // group whose tree is (being) loaded
+            auto use_group = [&](int g) {   // -> range index of the tiles that follow
+                if (g != cur_g) {
+                    // every tile of the previous range has to be retired before its tree is overwritten
+                    while (t_retire < t_issue) retire(t_retire++);
+                    // ... and the previous tree has to have arrived (an unused prefetch may still be in flight)
+                    if (n_trees > 0) mbar_wait(bar_tree, (unsigned)(n_trees - 1) & 1u);
+                    mbar_arrive_expect_tx(bar_tree, kTreeBytes);
+                    bulk_load(sm0, a.packed + (size_t)a.n_groups * kPadEntries * VBQ_GROUP + (size_t)g * kWalkFloats, kTreeBytes,
+                              bar_tree);
+                    ++n_trees;
+                    cur_g = g;
                 }
-                ++range;
+                return n_trees - 1;
+            };
+            if (a.queue == nullptr) {
+                // static shares: rows [p0, p1) of the (group, row) order
+                for (long long pos = p0; pos < p1;) {
+                    int g, row_a, row_b;
+                    next_range(pos, g, row_a, row_b);
+                    const int range = use_group(g);
+                    for (int r0 = row_a; r0 < row_b; r0 += kTmaRows) {
+                        if (t_issue - t_retire == S) retire(t_retire++);
+                        load(t_issue++, g, r0, min(kTmaRows, min(row_b, rows) - r0), range);
+                    }
+                }
+            } else {
+                // dynamic: every group is a queue of 128-row tiles (one global counter each).  A CTA starts with its home
+                // group and, when that queue is empty, moves to a group nobody has touched yet or one with enough work left
+                // to be worth a second tree; whoever has touched a queue stays until it is empty, so nothing is left over.
+                const unsigned n_tiles_g = (unsigned)((rows + kTmaRows - 1) / kTmaRows);
+                const unsigned worth = max(2u, 3u * gridDim.x / (2u * (unsigned)a.n_groups));
+                int g = home_g;
+                unsigned idx = queue_claim(a.queue + g);
+                for (;;) {
+                    if (idx >= n_tiles_g) {
+                        int found = -1;
+                        for (int j = 1; j < a.n_groups && found < 0; ++j) {
+                            const int g2 = g + j < a.n_groups ? g + j : g + j - a.n_groups;
+                            const unsigned taken = queue_peek(a.queue + g2);
+                            if (taken == 0u || (taken < n_tiles_g && n_tiles_g - taken > worth)) found = g2;
+                        }
+                        if (found < 0) break;
+                        g = found;
+                        idx = queue_claim(a.queue + g);
+                        continue;
+                    }
+                    const int range = use_group(g);
+                    if (t_issue - t_retire == S) retire(t_retire++);
+                    const int r0 = (int)idx * kTmaRows;
+                    load(t_issue++, g, r0, min(kTmaRows, rows - r0), range);
+                    idx = queue_claim(a.queue + g);   // in flight while the consumers work
+                }
             }
             while (t_retire < t_issue) retire(t_retire++);
             // every store has READ its slot (retire waits for that), which is all the CTA owes the copies before it
-            // exits; their global writes complete before the grid does
+            // exits; their global writes complete before the grid does.  Stop signs for the tickets still in flight (a
+            // warp holds at most two: fewer than S tiles in all).
+            for (int j = 0; j < S; ++j) {
+                const int s_ = (t_issue + j) & (S - 1);
+                sts_v4(sm0 + kOffDesc + 16 * s_, -1, 0, 0, 0);
+                mbar_arrive(bar_full + 8 * s_);
+            }
         }
         __syncwarp();
     } else {
@@ -498,9 +556,8 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
         };
 
         auto run = [&](auto lv_tag) {
-            const int n_tickets = (int)lds_u32i(sm0 + kOffNext + 4);
             int kk = __shfl_sync(0xffffffffu, claim_ticket(sm0 + kOffNext, lane), 0);
-            while (kk < n_tickets) {
+            for (;;) {
                 // the next ticket one iteration ahead; its value is read at the end of this iteration, so the atomic's
                 // latency never stalls the warp
                 const int nxt_raw = claim_ticket(sm0 + kOffNext, lane);
@@ -510,6 +567,7 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
                     cur_tile = tile;
                     mbar_wait_sleepy(bar_full + sb, ((unsigned)tile >> 2) & 1u, 20000u);
                     const int4 d = lds_v4(sm0 + kOffDesc + 2 * sb);
+                    if (d.x < 0) break;   // stop sign: no more tiles
                     valid = d.x;
                     if (d.y != range) {   // a new range: its tree, first code point and channel
                         range = d.y;
@@ -553,9 +611,41 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc_dist += __shfl_xor_sync(0xffffffffu, acc_dist, o);
         }
-        // acc_dist < 2^53 converts exactly; the sums over the CTAs are then sums of multiples of 2^-24
-        const double v[VBQ_TOTALS] = {(double)acc_level, (double)acc_level, 0.0, (double)acc_dist * (1.0 / 16777216.0)};
-        publish_totals<32 * (W + 1)>(a, 0, v, sRed, &sLast);
+        // integer partials of the CTAs, added by the last CTA to arrive (ticket counter): exact, so neither the arrival
+        // order nor the distribution of the tiles over the CTAs matters
+        long long *part = reinterpret_cast<long long *>(a.partials);
+        if (threadIdx.x == 0) {
+            part[2 * blockIdx.x] = acc_level;
+            part[2 * blockIdx.x + 1] = (long long)acc_dist;
+            unsigned t;   // release: the partials above are visible to whoever acquires the counter after this increment
+            asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(t) : "l"(a.ticket) : "memory");
+            sLast = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (sLast && warp == 0) {
+            __threadfence();
+            const volatile long long *vp = part;
+            long long lv = 0, ds = 0;
+            for (unsigned b = lane; b < gridDim.x; b += 32) {
+                lv += vp[2 * b];
+                ds += vp[2 * b + 1];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lv += __shfl_xor_sync(0xffffffffu, lv, o);
+                ds += __shfl_xor_sync(0xffffffffu, ds, o);
+            }
+            if (lane == 0) {
+                const double l_ = (double)lv, d_ = (double)ds * (1.0 / 16777216.0);
+                a.totals[0] = a.accumulate ? a.totals[0] + l_ : l_;
+                a.totals[1] = a.accumulate ? a.totals[1] + l_ : l_;
+                a.totals[2] = a.accumulate ? a.totals[2] : 0.0;
+                a.totals[3] = a.accumulate ? a.totals[3] + d_ : d_;
+                a.ticket[0] = 0u;
+            }
+            if (a.queue)
+                for (int g = lane; g < a.n_groups; g += 32) a.queue[g] = 0u;
+        }
     }
 #ifdef VBQ_TRACE
     if (threadIdx.x == 0) tr[4] = (double)gtime();

@@ -27,6 +27,7 @@ FLAG_RESERVE_SM = _lib.FLAG_RESERVE_SM
 FLAG_BRACKET_WALK = _lib.FLAG_BRACKET_WALK
 FLAG_WORKSPACE_ZEROED = _lib.FLAG_WORKSPACE_ZEROED
 FLAG_NO_TMA = _lib.FLAG_NO_TMA
+FLAG_TABLE_STABLE = _lib.FLAG_TABLE_STABLE
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -64,6 +65,17 @@ def _host_penalty_ptr(penalty):
     if host is None or tuple(host.shape) != tuple(penalty.shape):
         return None
     return host.ctypes.data
+
+
+def stable_packed(packed):
+    """Mark a packed table as complete: the caller has synchronized since vbq_pack_code_points wrote it, so the search
+    kernels may read it before earlier kernels of the stream have finished (VBQ_FLAG_TABLE_STABLE).  Returns `packed`."""
+    packed._vbq_stable = True
+    return packed
+
+
+def _table_flags(packed, flags):
+    return flags | FLAG_TABLE_STABLE if getattr(packed, "_vbq_stable", False) else flags
 
 
 def search_flags(lambs, flags=0):
@@ -129,7 +141,7 @@ def quantize_into(mu, sigma, table, packed, penalty, length, entropy_model, max_
     st = lib.vbq_quantize_hp(_ptr(mu), _ptr(sigma), rows, C, _ptr(table), _ptr(packed), max_bits,
                              _ptr(penalty), _host_penalty_ptr(penalty), _ptr(length), n_lambda, pen_channels,
                              _ptr(entropy_model), _ptr(zhat), _ptr(qidx), _ptr(level), _ptr(bits), _ptr(em_bits),
-                             _ptr(totals), _ptr(workspace), ws_bytes, flags, _stream(mu.device))
+                             _ptr(totals), _ptr(workspace), ws_bytes, _table_flags(packed, flags), _stream(mu.device))
     _lib.check(st, "vbq_quantize_hp")
 
 
@@ -163,7 +175,7 @@ class QuantizePlan:
                        _host_penalty_ptr(penalty),
                        _ptr(length), n_lambda, pen_channels, _ptr(entropy_model), _ptr(zhat), _ptr(qidx), _ptr(level),
                        _ptr(bits), _ptr(em_bits), _ptr(totals), _ptr(ws),
-                       0 if ws is None else ws.numel() * ws.element_size(), self._kw["flags"])
+                       0 if ws is None else ws.numel() * ws.element_size(), _table_flags(packed, self._kw["flags"]))
         self._graph = None
         if graph:
             torch.cuda.synchronize(mu.device)
@@ -411,7 +423,7 @@ class HostPipeline:
                 _host_ptr(zhat, torch.float32, o, "zhat"), _host_ptr(qidx, torch.int32, o, "qidx"),
                 _host_ptr(level, torch.int32, o, "level"), _host_ptr(bits, torch.float32, o, "bits"),
                 _host_ptr(em_bits, torch.float32, o, "em_bits"),
-                _host_ptr(totals, torch.float64, (L, _lib.TOTALS), "totals"), flags)
+                _host_ptr(totals, torch.float64, (L, _lib.TOTALS), "totals"), _table_flags(packed, flags))
         _lib.check(st, "vbq_quantize_host")
 
     def close(self):

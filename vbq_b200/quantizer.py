@@ -55,6 +55,8 @@ class ChannelwisePriorCDFQuantizer:
         self.all_code_points = t
         self.code_points_by_channel = torch.sort(t, dim=1).values       # MUST BE SORTED (quantizer.py:37)
         self._packed = ops.pack_code_points(t, self.max_bits_per_coord)
+        torch.cuda.current_stream(t.device).synchronize()   # like the reference, building the tables is a blocking call
+        ops.stable_packed(self._packed)                     # ... so the search kernels may prefetch them (ops.stable_packed)
         self._cache = {}
 
     @property

@@ -48,6 +48,8 @@ class GaussianCodebook:
         self.lengths = np.concatenate([np.full(2 ** n, n, dtype=np.int64) for n in range(N + 1)])
         self._table = pts.to(torch.float32).reshape(1, -1).repeat(_VC, 1).contiguous()   # (16, Q)
         self._packed = ops.pack_code_points(self._table, N)
+        torch.cuda.current_stream(self._table.device).synchronize()
+        ops.stable_packed(self._packed)
 
     def _level_lengths(self, bitlengths):
         N = self.max_codepoint_length
