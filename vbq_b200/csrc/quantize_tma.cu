@@ -178,7 +178,7 @@ static __device__ __forceinline__ int reference_search_warp(const float *sSc, co
 // NT > 0: max_bits_per_coord == NT at compile time; NT == 0: run time (<= kSmemDepth).
 // W = consumer warps (the CTA has W + 1 warps); P = coordinate pairs per thread: a warp iteration ("unit") covers
 // 4P consecutive rows x 16 channels, lane = (row parity, channel), coordinates at rows parity + 2u, u < 2P.
-template <bool TOTALS, int NT, int OUT, int W, int P>
+template <bool PRUNE, bool TOTALS, int NT, int OUT, int W, int P>
 __global__ void __launch_bounds__(32 * (W + 1), 1)
     vbq_bisect_tma_kernel(const QArgs a, const __grid_constant__ TmaMaps maps, const UniformPen up) {
     constexpr int U = 2 * P, S = kSlots;
@@ -464,11 +464,33 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
                 }
             };
             int m_done = 0;   // deepest depth visited
+            // sound early exit (PRUNE): every deeper key is >= key(pen_n), so the walk may stop once the best key so far
+            // is more than the certificate's guard below it for every coordinate of the warp (tested every third depth)
+            unsigned run_min[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) run_min[u] = 0xffffffffu;
+            auto prune_here = [&](auto n_tag) -> bool {
+                constexpr int n = decltype(n_tag)::value;
+                const unsigned floor_key = __float_as_uint(up.v[n]) & kmask;
+                bool done = floor_key > kKeyGuard + 32u;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    run_min[u] = __vimin3_u32(run_min[u], key[u][n - 3], key[u][n - 2]);
+                    run_min[u] = min(run_min[u], key[u][n - 1]);
+                    done = done && run_min[u] < floor_key - (kKeyGuard + 32u);
+                }
+                return __all_sync(0xffffffffu, done);
+            };
+            bool stop = false;
 #define VBQ_DEPTH(n_)                                                                                          \
     if constexpr (n_ <= kSmemDepth) {                                                                          \
-        if (NT > 0 ? n_ <= NT : n_ <= N) {                                                                     \
-            depth(std::integral_constant<int, n_>{});                                                          \
-            m_done = n_;                                                                                       \
+        if ((NT > 0 ? n_ <= NT : n_ <= N) && !stop) {                                                          \
+            if (PRUNE && (n_ <= 9 && n_ % 3 == 0) && prune_here(std::integral_constant<int, n_>{})) {          \
+                stop = true;                                                                                   \
+            } else {                                                                                           \
+                depth(std::integral_constant<int, n_>{});                                                      \
+                m_done = n_;                                                                                   \
+            }                                                                                                  \
         }                                                                                                      \
     }
             VBQ_DEPTH(1) VBQ_DEPTH(2) VBQ_DEPTH(3) VBQ_DEPTH(4) VBQ_DEPTH(5)
@@ -688,7 +710,7 @@ int vbq_make_tensor_map(CUtensorMap *out, const void *base, int C, long long row
 
 static_assert(vbq_walk_tree_floats(1) == kWalkFloats, "layout of the walk tree (tree.cuh, quantize.cu)");
 
-template <bool TOTALS, int NT, int OUT, int W, int P>
+template <bool PRUNE, bool TOTALS, int NT, int OUT, int W, int P>
 static int launch_tma(const QArgs &a0, const void *out0, const void *out1, int dev, int sms, cudaStream_t st) {
     constexpr int kTile = kTmaRows;
     const long long rows4 = (a0.rows + 3) & ~3ll;
@@ -696,7 +718,7 @@ static int launch_tma(const QArgs &a0, const void *out0, const void *out1, int d
     gx = gx < sms ? gx : sms;
     if (gx > kMaxGrid) gx = kMaxGrid;
     if (gx < 1) gx = 1;
-    auto kern = vbq_bisect_tma_kernel<TOTALS, NT, OUT, W, P>;
+    auto kern = vbq_bisect_tma_kernel<PRUNE, TOTALS, NT, OUT, W, P>;
     VBQ_ENSURE_MAX_SMEM(kern, dev);
     static_assert(((size_t)kWalkFloats + (size_t)kSlots * 2 * kTile * VBQ_GROUP) * sizeof(float) + 512 == kTmaSmemBytes, "slots");
     const size_t smem = kTmaSmemBytes;
@@ -736,37 +758,37 @@ static int launch_tma(const QArgs &a0, const void *out0, const void *out1, int d
 
 constexpr int kConsumerWarps = 19, kPairs = 2;   // measured: 31x1 46.7, 23x1 46.1, 15x2 45.0, 17x2 44.9, 19x2 43.4, 21x2 45.1 (spills), 11x4 48.5 us per Kodak step
 
-template <bool TOTALS, int NT>
+template <bool PRUNE, bool TOTALS, int NT>
 static int launch_tma3(const QArgs &a, int dev, int sms, cudaStream_t st) {
     constexpr int W = kConsumerWarps, P = kPairs;
 #ifdef VBQ_DEV_VARIANTS   // development: geometry variants of the benchmark's kernel, chosen by VBQ_TMA_VARIANT
-    if constexpr (TOTALS && NT == 10) {
+    if constexpr (!PRUNE && TOTALS && NT == 10) {
         const char *v = getenv("VBQ_TMA_VARIANT");
         const int vi = v ? atoi(v) : 0;
         if ((a.outm & 15u) == (2u | 8u) && vi > 0) {
-            if (vi == 1) return launch_tma<true, 10, 2 | 8, 17, 2>(a, a.qidx, a.bits, dev, sms, st);
-            if (vi == 2) return launch_tma<true, 10, 2 | 8, 21, 2>(a, a.qidx, a.bits, dev, sms, st);
-            if (vi == 3) return launch_tma<true, 10, 2 | 8, 19, 2>(a, a.qidx, a.bits, dev, sms, st);
-            if (vi == 4) return launch_tma<true, 10, 2 | 8, 23, 2>(a, a.qidx, a.bits, dev, sms, st);
-            if (vi == 5) return launch_tma<true, 10, 2 | 8, 11, 4>(a, a.qidx, a.bits, dev, sms, st);
-            if (vi == 6) return launch_tma<true, 10, 2 | 8, 13, 4>(a, a.qidx, a.bits, dev, sms, st);
-            if (vi == 7) return launch_tma<true, 10, 2 | 8, 9, 4>(a, a.qidx, a.bits, dev, sms, st);
+            if (vi == 1) return launch_tma<false, true, 10, 2 | 8, 17, 2>(a, a.qidx, a.bits, dev, sms, st);
+            if (vi == 2) return launch_tma<false, true, 10, 2 | 8, 21, 2>(a, a.qidx, a.bits, dev, sms, st);
+            if (vi == 3) return launch_tma<false, true, 10, 2 | 8, 19, 2>(a, a.qidx, a.bits, dev, sms, st);
+            if (vi == 4) return launch_tma<false, true, 10, 2 | 8, 23, 2>(a, a.qidx, a.bits, dev, sms, st);
+            if (vi == 5) return launch_tma<false, true, 10, 2 | 8, 11, 4>(a, a.qidx, a.bits, dev, sms, st);
+            if (vi == 6) return launch_tma<false, true, 10, 2 | 8, 13, 4>(a, a.qidx, a.bits, dev, sms, st);
+            if (vi == 7) return launch_tma<false, true, 10, 2 | 8, 9, 4>(a, a.qidx, a.bits, dev, sms, st);
         }
     }
 #endif
 #ifdef VBQ_DEV_ONE   // development builds: only the benchmark's variant (fast compile, small SASS listing)
-    if constexpr (TOTALS && NT == 10) {
-        if ((a.outm & 15u) == (2u | 8u)) return launch_tma<true, 10, 2 | 8, W, P>(a, a.qidx, a.bits, dev, sms, st);
+    if constexpr (!PRUNE && TOTALS && NT == 10) {
+        if ((a.outm & 15u) == (2u | 8u)) return launch_tma<false, true, 10, 2 | 8, W, P>(a, a.qidx, a.bits, dev, sms, st);
     }
     return -1;
 #else
     switch (a.outm & 15u) {
-        case 2u | 8u: return launch_tma<TOTALS, NT, 2 | 8, W, P>(a, a.qidx, a.bits, dev, sms, st);
-        case 1u | 4u: return launch_tma<TOTALS, NT, 1 | 4, W, P>(a, a.zhat, a.level, dev, sms, st);
-        case 1u: return launch_tma<TOTALS, NT, 1, W, P>(a, a.zhat, nullptr, dev, sms, st);
-        case 2u: return launch_tma<TOTALS, NT, 2, W, P>(a, a.qidx, nullptr, dev, sms, st);
+        case 2u | 8u: return launch_tma<PRUNE, TOTALS, NT, 2 | 8, W, P>(a, a.qidx, a.bits, dev, sms, st);
+        case 1u | 4u: return launch_tma<PRUNE, TOTALS, NT, 1 | 4, W, P>(a, a.zhat, a.level, dev, sms, st);
+        case 1u: return launch_tma<PRUNE, TOTALS, NT, 1, W, P>(a, a.zhat, nullptr, dev, sms, st);
+        case 2u: return launch_tma<PRUNE, TOTALS, NT, 2, W, P>(a, a.qidx, nullptr, dev, sms, st);
         case 0u:
-            if constexpr (TOTALS) return launch_tma<TOTALS, NT, 0, W, P>(a, nullptr, nullptr, dev, sms, st);
+            if constexpr (TOTALS) return launch_tma<PRUNE, TOTALS, NT, 0, W, P>(a, nullptr, nullptr, dev, sms, st);
             return -1;
         default: return -1;
     }
@@ -790,6 +812,11 @@ int vbq_launch_quantize_tma(const QArgs &a, int dev, int sms, cudaStream_t st) {
             prev = p;
         }
     }
-    if (a.N == kSmemDepth) return a.totals ? launch_tma3<true, kSmemDepth>(a, dev, sms, st) : launch_tma3<false, kSmemDepth>(a, dev, sms, st);
-    return a.totals ? launch_tma3<true, 0>(a, dev, sms, st) : launch_tma3<false, 0>(a, dev, sms, st);
+    // results do not depend on the early-exit tests, so only the common case (compile-time depth) is compiled without them
+    const bool prune = !(a.flags & VBQ_FLAG_NO_PRUNE);
+    if (a.N == kSmemDepth) {
+        if (prune) return a.totals ? launch_tma3<true, true, kSmemDepth>(a, dev, sms, st) : launch_tma3<true, false, kSmemDepth>(a, dev, sms, st);
+        return a.totals ? launch_tma3<false, true, kSmemDepth>(a, dev, sms, st) : launch_tma3<false, false, kSmemDepth>(a, dev, sms, st);
+    }
+    return a.totals ? launch_tma3<true, true, 0>(a, dev, sms, st) : launch_tma3<true, false, 0>(a, dev, sms, st);
 }
