@@ -165,7 +165,8 @@ int vbq_host_ctx_destroy(vbq_host_ctx *ctx);
  * h_mu / h_sigma are (rows, C); outputs are (n_lambda, rows, C) host arrays (NULL to skip; must have been
  * selected at context creation); h_totals is (n_lambda, VBQ_TOTALS).  Tables, penalties and entropy models are
  * device pointers as in vbq_quantize.  Rows are processed in chunks whose upload, kernel and download overlap on
- * three streams; the call returns when all results are in host memory. */
+ * three streams of the context; the call returns when all results are in host memory.  The d_* tables must be
+ * complete when the call is made (it does not order itself after other streams). */
 int vbq_quantize_host(vbq_host_ctx *ctx, const float *h_mu, const float *h_sigma, long long rows,
                       const float *d_table, const float *d_packed, const float *d_penalty, const float *d_length,
                       int pen_channels, const float *d_entropy_model,

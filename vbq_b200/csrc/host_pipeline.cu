@@ -115,6 +115,15 @@ extern "C" int vbq_quantize_host(vbq_host_ctx *c, const float *h_mu, const float
         return vbq_fail(VBQ_ERR_BAD_FLAGS, "vbq_quantize_host: VBQ_FLAG_ACCUMULATE_TOTALS is managed internally");
     const int C = c->C, L = c->n_lambda;
     const size_t row_bytes = (size_t)C * sizeof(float);
+    // Channel-independent penalties also travel as launch constants (vbq_quantize_hp): fetch the few bytes once.  The
+    // tables are the caller's: they must be complete when this (synchronous) call is made, see include/vbq_b200.h.
+    float h_pen[64];
+    const float *pen_host = nullptr;
+    if (pen_channels == 1 && (size_t)L * (c->N + 1) <= 64 && d_penalty && rows > 0) {
+        CUDA_TRY(cudaMemcpyAsync(h_pen, d_penalty, (size_t)L * (c->N + 1) * sizeof(float), cudaMemcpyDeviceToHost, c->s_k));
+        CUDA_TRY(cudaStreamSynchronize(c->s_k));
+        pen_host = h_pen;
+    }
     long long k = 0;
     for (long long r0 = 0; r0 < rows; r0 += c->chunk_rows, ++k) {
         const long long nr = rows - r0 < c->chunk_rows ? rows - r0 : c->chunk_rows;
@@ -127,7 +136,7 @@ extern "C" int vbq_quantize_host(vbq_host_ctx *c, const float *h_mu, const float
         // kernel
         CUDA_TRY(cudaStreamWaitEvent(c->s_k, s.in, 0));
         if (k >= kSlots) CUDA_TRY(cudaStreamWaitEvent(c->s_k, s.out, 0));
-        RETURN_IF(vbq_quantize(s.mu, s.sigma, nr, C, d_table, d_packed, c->N, d_penalty, d_length, L, pen_channels,
+        RETURN_IF(vbq_quantize_hp(s.mu, s.sigma, nr, C, d_table, d_packed, c->N, d_penalty, pen_host, d_length, L, pen_channels,
                                d_entropy_model, h_zhat ? s.zhat : nullptr, h_qidx ? s.qidx : nullptr,
                                h_level ? s.level : nullptr, h_bits ? s.bits : nullptr,
                                h_em_bits ? s.em_bits : nullptr, h_totals ? c->d_totals : nullptr, c->d_ws, c->ws_bytes,
@@ -137,14 +146,19 @@ extern "C" int vbq_quantize_host(vbq_host_ctx *c, const float *h_mu, const float
         // download: (n_lambda, nr, C) device block -> rows [r0, r0+nr) of each lambda plane of the host array
         CUDA_TRY(cudaStreamWaitEvent(c->s_out, s.done, 0));
         const size_t w = nr * row_bytes, hp = (size_t)rows * row_bytes;
+        const size_t max_pitch = 0x7fffffffull;   // cudaDeviceProp::memPitch of every current device
 #define D2H(hp_, dp_)                                                                                         \
     if (hp_) {                                                                                                \
         if (L == 1)                                                                                           \
             CUDA_TRY(cudaMemcpyAsync((char *)(hp_) + (size_t)r0 * row_bytes, dp_, w, cudaMemcpyDeviceToHost,  \
                                      c->s_out));                                                              \
-        else                                                                                                  \
+        else if (hp <= max_pitch)                                                                             \
             CUDA_TRY(cudaMemcpy2DAsync((char *)(hp_) + (size_t)r0 * row_bytes, hp, dp_, w, w, (size_t)L,      \
                                        cudaMemcpyDeviceToHost, c->s_out));                                    \
+        else /* lambda planes further apart than the largest 2-D pitch: one copy per plane */                \
+            for (int l_ = 0; l_ < L; ++l_)                                                                    \
+                CUDA_TRY(cudaMemcpyAsync((char *)(hp_) + (size_t)l_ * hp + (size_t)r0 * row_bytes,            \
+                                         (const char *)(dp_) + (size_t)l_ * w, w, cudaMemcpyDeviceToHost, c->s_out)); \
     }
         D2H(h_zhat, s.zhat);
         D2H(h_qidx, s.qidx);

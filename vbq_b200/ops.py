@@ -416,6 +416,8 @@ class HostPipeline:
             raise ValueError("vbq_b200: penalty must be (n_lambda, 1 or C, N+1)")
         o = (L, rows, C)
         with torch.cuda.device(self.device):
+            # the pipeline runs on its own streams: whatever produced the tables on this thread's stream has to be done
+            torch.cuda.current_stream(self.device).synchronize()
             st = self._lib.vbq_quantize_host(
                 self._h, _host_ptr(h_mu, torch.float32, (rows, C), "h_mu"),
                 _host_ptr(h_sigma, torch.float32, (rows, C), "h_sigma"), rows, _ptr(table), _ptr(packed),

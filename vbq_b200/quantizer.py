@@ -30,6 +30,7 @@ class ChannelwisePriorCDFQuantizer:
         self.code_points_by_channel = None
         self._packed = None
         self._cache = {}
+        self._pipes = {}
 
     # ------------------------------------------------------------------------------------------------
     # code points (reference quantizer.py:25-63)
@@ -129,6 +130,53 @@ class ChannelwisePriorCDFQuantizer:
                                             self.max_bits_per_coord, outputs, flags)
         return dict(zhat=z, qidx=q, level=lv, bits=b, em_bits=eb, totals=tot)
 
+    # ------------------------------------------------------------------------------------------------
+    # host arrays in, host arrays out: the chunked upload / kernel / download pipeline (vbq_quantize_host)
+    # ------------------------------------------------------------------------------------------------
+    _HOST_CHUNK_ROWS = 9216
+
+    @staticmethod
+    def _is_host(x):
+        return isinstance(x, np.ndarray) or (isinstance(x, torch.Tensor) and not x.is_cuda)
+
+    def _quantize_host(self, means, scales, lambs, outputs, logvar=False, entropy_bits=False):
+        """means / scales: host arrays (rows, C).  Returns a dict of pinned host tensors (len(lambs), rows, C) for the
+        requested outputs.  Same results as `quantize` on device tensors (tests/test_gpu_parity.py)."""
+        C, N, L = self.num_channels, self.max_bits_per_coord, len(lambs)
+
+        def host_f32(x):
+            t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+            return t.to(torch.float32).reshape(-1, C).contiguous()
+
+        m, s = host_f32(means), host_f32(scales)
+        rows = int(m.shape[0])
+        pen, length = self._length_tables(lambs)
+        em = None
+        if entropy_bits:
+            if self.entropy_models is None:
+                raise TypeError("'NoneType' object is not subscriptable: entropy_models not built "
+                                "(call build_entropy_models first)")
+            em = self._entropy_model_tensor(lambs)
+            outputs |= ops.OUT_EM_BITS
+        key = ("pipe", L, outputs)
+        pipes = self.__dict__.setdefault('_pipes', {})
+        if key not in pipes:
+            # three staging slots of `chunk` rows: inputs plus every selected output for every lambda; <= 64 MB per slot
+            n_out = bin(outputs & (ops.OUT_ZHAT | ops.OUT_QIDX | ops.OUT_LEVEL | ops.OUT_BITS | ops.OUT_EM_BITS)).count("1")
+            chunk = int(min(self._HOST_CHUNK_ROWS, max(256, (64 << 20) // (4 * C * (2 + n_out * L)))))
+            pipes[key] = ops.HostPipeline(C, N, L, chunk, outputs, device=self.device)
+        flags = ops.search_flags(lambs, ops.FLAG_LOGVAR if logvar else 0)
+        bufs = {}
+        for name, bit, dt in (("zhat", ops.OUT_ZHAT, torch.float32), ("qidx", ops.OUT_QIDX, torch.int32),
+                              ("level", ops.OUT_LEVEL, torch.int32), ("bits", ops.OUT_BITS, torch.float32),
+                              ("em_bits", ops.OUT_EM_BITS, torch.float32)):
+            if outputs & bit:
+                bufs[name] = torch.empty((L, rows, C), dtype=dt, pin_memory=True)
+        if outputs & ops.OUT_TOTALS:
+            bufs["totals"] = torch.empty((L, 4), dtype=torch.float64, pin_memory=True)
+        pipes[key].run(m, s, self.all_code_points, self._packed, pen, length, em, flags=flags, **bufs)
+        return bufs
+
     def _prep(self, means, scales):
         C = self.num_channels
         m = utils.as_device_f32(means, self.device).reshape(-1, C)
@@ -141,12 +189,19 @@ class ChannelwisePriorCDFQuantizer:
         n + R_lambda[c, n] (float32).  kwargs: ``return_np`` (default True, as utils.py:363)."""
         return_np = kwargs.get('return_np', True)
         B, C = batch_means.shape
-        m, s = self._prep(batch_means, batch_stds)
         corrected = bool(self.raw_code_length_entropy_models)
-        out = self.quantize(m, s, lambs, outputs=ops.OUT_ZHAT | (ops.OUT_BITS if corrected else ops.OUT_LEVEL))
-        zs, nbs = out['zhat'], (out['bits'] if corrected else out['level'])
-        if return_np:                      # one device-to-host copy per output, then per-lambda views
-            zs, nbs = utils.to_host_numpy(zs), utils.to_host_numpy(nbs)
+        want = ops.OUT_ZHAT | (ops.OUT_BITS if corrected else ops.OUT_LEVEL)
+        if return_np and self._is_host(batch_means) and self._is_host(batch_stds):
+            # host arrays in and out (the reference's call on NumPy inputs): upload, search and download overlap chunk
+            # by chunk instead of three whole-array passes
+            out = self._quantize_host(batch_means, batch_stds, lambs, want)
+            zs, nbs = out['zhat'].numpy(), (out['bits'] if corrected else out['level']).numpy()
+        else:
+            m, s = self._prep(batch_means, batch_stds)
+            out = self.quantize(m, s, lambs, outputs=want)
+            zs, nbs = out['zhat'], (out['bits'] if corrected else out['level'])
+            if return_np:                      # one device-to-host copy per output, then per-lambda views
+                zs, nbs = utils.to_host_numpy(zs), utils.to_host_numpy(nbs)
         Z_hat_dict, num_bits_dict = {}, {}
         for i, lamb in enumerate(lambs):
             Z_hat_dict[lamb] = zs[i]
@@ -188,6 +243,17 @@ class ChannelwisePriorCDFQuantizer:
 
     def compress_latents(self, posterior_means, posterior_logvars, lambs):
         """Reference quantizer.py:190-240.  sigma = sqrt(exp(logvar)) is computed inside the kernel."""
+        if self._is_host(posterior_means) and self._is_host(posterior_logvars):
+            C = int(posterior_logvars.shape[-1])
+            assert C == self.num_channels
+            shape = (len(lambs),) + tuple(posterior_means.shape)
+            corrected = bool(self.raw_code_length_entropy_models)
+            out = self._quantize_host(posterior_means, posterior_logvars, lambs,
+                                      ops.OUT_ZHAT | (ops.OUT_BITS if corrected else ops.OUT_LEVEL), logvar=True,
+                                      entropy_bits=True)
+            host = dict(Z_hat=out['zhat'].reshape(shape), raw_num_bits=(out['bits'] if corrected else out['level']).reshape(shape),
+                        num_bits=out['em_bits'].reshape(shape), corrected=corrected)
+            return self._latents_to_host(host, lambs)
         return self._latents_to_host(self._compress_latents_device(posterior_means, posterior_logvars, lambs), lambs)
 
     def compress(self, X, vae, lambs, clip=True):
@@ -279,6 +345,7 @@ class ChannelwisePriorCDFQuantizer:
         d['code_points_by_channel'] = None
         d['_packed'] = None
         d['_cache'] = {}
+        d['_pipes'] = {}
         d['device'] = str(self.device)
         return d
 

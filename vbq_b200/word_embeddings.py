@@ -87,6 +87,58 @@ class GaussianCodebook:
 
         return dict(zhat=unpad(z), qidx=unpad(q), level=unpad(lv), bits=unpad(b), totals=tot)
 
+    def beta_sweep(self, means, stds, betas, exact=False, reduce_fn=None, max_chunk_symbols=1 << 29):
+        """The rate side of the notebook's beta sweep (ipynb:464-473, :1102-1103: `test_beta` for every beta of
+        `np.exp(np.linspace(np.log(0.01), np.log(100000), 50))`): compresses all coordinates with every beta and
+        returns the `compressed_bitlength` = `empirical_entropy(compressed)` (ipynb:452-455) of each, as a float64
+        array (the embedding-quality metrics of `test_beta` need the skip-gram model and are out of scope).
+
+        The coordinates are walked ONCE for all betas (sweep kernel) in row chunks of at most ``max_chunk_symbols``
+        (beta, coordinate) pairs; the symbols of a chunk are counted on the device (`vbq_symbol_histogram`) and only the
+        (len(betas), Q) count table leaves the loop.  ``exact=True`` runs the notebook's float64 search once per beta
+        instead.  ``reduce_fn`` (optional) all-reduces the int64 counts over row-sharded ranks
+        (`vbq_b200.sharding.all_reduce_counts`) before the entropies are formed."""
+        N, Q = self.max_codepoint_length, 2 ** (self.max_codepoint_length + 1) - 1
+        m = (means if isinstance(means, torch.Tensor) else torch.as_tensor(np.asarray(means)))
+        s = (stds if isinstance(stds, torch.Tensor) else torch.as_tensor(np.asarray(stds)))
+        m = m.to(device=self.device, dtype=torch.float32).reshape(-1)
+        s = s.to(device=self.device, dtype=torch.float32).reshape(-1)
+        betas = [float(b) for b in betas]
+        L, n = len(betas), m.numel()
+        counts = torch.zeros((L, _VC, Q), dtype=torch.int64, device=self.device)
+        if exact:
+            cp = torch.from_numpy(self.codepoints).to(self.device)
+            per_level = torch.from_numpy(self._level_lengths(self.lengths).astype(np.float64)).to(self.device)
+            step = max(_VC, (max_chunk_symbols // _VC) * _VC)
+            for i, beta in enumerate(betas):
+                for a in range(0, n, step):
+                    b = min(n, a + step)
+                    _, heap, level = ops.compress_coordinates_f64(m[a:b], s[a:b], cp, per_level, beta, True,
+                                                                  want_index=True, want_level=True)
+                    # heap index h of depth d -> sorted index (2 i + 1) 2^(N-d) - 1 with i = h - (2^d - 1)
+                    i_in = heap - ((1 << level) - 1)
+                    q = ((2 * i_in + 1) << (N - level)) - 1
+                    flat = torch.bincount(q.reshape(-1).long(), minlength=Q)
+                    counts[i, 0] += flat
+        else:
+            step = max(_VC, (max_chunk_symbols // max(L, 1) // _VC) * _VC)
+            for a in range(0, n, step):
+                b = min(n, a + step)
+                k = ((b - a) // _VC) * _VC
+                q = self.quantize(m[a:b], s[a:b], betas, outputs=ops.OUT_QIDX)['qidx']        # (L, b - a)
+                for i in range(L):
+                    if k:
+                        ops.symbol_histogram(q[i, :k].reshape(-1, _VC).contiguous(), N, counts[i])
+                    if k < b - a:     # the ragged tail (fewer than 16 symbols)
+                        counts[i, 0] += torch.bincount(q[i, k:].long(), minlength=Q)
+        counts = counts.sum(dim=1)
+        if reduce_fn is not None:
+            counts = reduce_fn(counts)
+        c = counts.double()
+        total = c.sum(dim=1)
+        plogp = torch.where(c > 0, c * torch.log2(c.clamp_min(1.0)), torch.zeros_like(c)).sum(dim=1)
+        return (total * torch.log2(total) - plogp).cpu().numpy()
+
     def compress_coordinates(self, means, stds, beta, bitlengths=None, exact=True):
         """Notebook signature (ipynb:429-443): returns (optima shaped and typed like `means`, None).
         Minimises (c - mu)^2 + 2 beta sigma^2 len(c) over the code points.
