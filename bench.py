@@ -8,8 +8,10 @@ A "step" is one pass of the hot path over one batch: the Kodak-shaped bls2017 la
 configs[1] (24 images x 32x48 x 192 channels = 7,077,888 coordinates, learned factorized prior at reference init,
 max_bits_per_coord=10, single lambda=0.5), written out as sorted quantile index (int32) + code length (float32)
 per coordinate, plus the per-lambda rate/distortion totals.  With N>1 every rank processes its own batch of that
-shape (weak scaling, no data-path collective) and the totals are all-reduced over NCCL inside the timed region
-(the totals of four consecutive steps per collective).
+shape (weak scaling, no data-path collective) and the totals are all-reduced over NCCL inside the timed region, once
+per call (`scaling_variants` also reports four calls per collective).  The same JSON line carries `corrected` (the
+reference's production mode: corrected code lengths + entropy-model bits) and `configs` (BASELINE.json configs[2..4]
+at this N through sharding.ShardedQuantizer).
 
 `value` is device-resident throughput (CUDA events, max over ranks); `e2e` goes through the reference-facing
 ChannelwisePriorCDFQuantizer.compress_batch_channel_latents-level call with pinned HOST buffers (H2D and D2H
@@ -267,6 +269,25 @@ def bind_to_gpu_numa_node(index):
 
 
 
+def _time_steps(fn, steps, warmup, barrier, finish=None):
+    """CUDA-event time of `steps` calls of fn(i) bracketed by barriers; returns milliseconds (this rank)."""
+    import torch
+    for i in range(warmup):
+        fn(i)
+    if finish:
+        finish()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for i in range(steps):
+        fn(warmup + i)
+    if finish:
+        finish()
+    ev[1].record()
+    barrier()
+    return ev[0].elapsed_time(ev[1])
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -282,6 +303,17 @@ def run_ours(args, rank, world, local_rank):
     if world > 1 and not args.no_reserve:
         args.flags |= ops.FLAG_RESERVE_SM               # leave one SM to the overlapped NCCL all-reduce
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # rotating buffer sets so that no step finds its inputs in the 126 MB L2
     set_bytes = COORDS * BYTES_PER_COORD
     n_sets = max(3, -(-3 * L2_BYTES // set_bytes))
@@ -291,122 +323,118 @@ def run_ours(args, rank, world, local_rank):
         sets.append(dict(mu=mu, sigma=sigma,
                          qidx=torch.empty((1, ROWS, C), dtype=torch.int32, device=dev),
                          bits=torch.empty((1, ROWS, C), dtype=torch.float32, device=dev)))
-    # one validated plan per (totals bucket, buffer set): a step is one prebound vbq_quantize call (one kernel launch
-    # incl. totals).  N > 1: the totals of n_sets consecutive steps form one bucket that is all-reduced with ONE NCCL call
-    # (asynchronous, on NCCL's own stream, overlapping the kernels of the next bucket); two buckets alternate, and a
-    # bucket is reused only after its previous all-reduce has finished (all inside the timed region).  Bucketing keeps
-    # most kernel boundaries free of stream operations, so that consecutive launches overlap (programmatic dependent
-    # launch) as they do on one GPU.
-    n_buckets = 2 if world > 1 else 1
-    buckets = [torch.zeros((n_sets, 1, 4), dtype=torch.float64, device=dev) for _ in range(n_buckets)]
-    plans = [[ops.QuantizePlan(b["mu"], b["sigma"], q.all_code_points, q._packed, pen, length, None, N_BITS,
-                               qidx=b["qidx"], bits=b["bits"], totals=buckets[k][s], flags=args.flags,
-                               graph=args.graph) for s, b in enumerate(sets)] for k in range(n_buckets)]
-    pending = [None] * n_buckets
-    last = {"i": -1}
 
-    def step(i):
-        last["i"] = i
-        k, s_ = (i // n_sets) % n_buckets, i % n_sets
-        if s_ == 0 and pending[k] is not None:
-            pending[k].wait()
-            pending[k] = None
-        t = plans[k][s_].run()
-        if world > 1 and s_ == n_sets - 1:
-            pending[k] = dist.all_reduce(buckets[k], op=dist.ReduceOp.SUM, async_op=True)
-        return t
+    # ---- headline: device-resident steps ---------------------------------------------------------------------------
+    # A step is one prebound vbq_quantize call = one kernel launch incl. the per-lambda totals.  N > 1: the (1, 4) totals
+    # are all-reduced over NCCL inside the timed region (sharding.all_reduce_totals, asynchronous on NCCL's stream,
+    # overlapping the next kernels): once per call (`collective_every` = 1, the headline) and, for comparison, the totals
+    # of n_sets consecutive calls in one collective.
+    def headline(every):
+        n_buckets = 2 if world > 1 else 1
+        buckets = [torch.zeros((every, 1, 4), dtype=torch.float64, device=dev) for _ in range(n_buckets)]
+        plans = [[[ops.QuantizePlan(b["mu"], b["sigma"], q.all_code_points, q._packed, pen, length, None, N_BITS,
+                                    qidx=b["qidx"], bits=b["bits"], totals=buckets[k][e], flags=args.flags,
+                                    graph=args.graph) for b in sets] for e in range(every)] for k in range(n_buckets)]
+        pending = [None] * n_buckets
+        last = {"i": -1}
 
-    def drain():
-        if world > 1:
-            for k in range(n_buckets):
-                if pending[k] is not None:
-                    pending[k].wait()
-                    pending[k] = None
-            # a partially filled last bucket (the run did not end on a bucket boundary) is reduced here
-            i = last["i"]
-            if i >= 0 and i % n_sets != n_sets - 1:
-                dist.all_reduce(buckets[(i // n_sets) % n_buckets], op=dist.ReduceOp.SUM)
-                last["i"] = -1
+        def step(i):
+            last["i"] = i
+            k, e = (i // every) % n_buckets, i % every
+            if e == 0 and pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
+            plans[k][e][i % n_sets].run()
+            if world > 1 and e == every - 1:
+                pending[k] = sharding.all_reduce_totals(buckets[k], async_op=True)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        def drain():
+            if world > 1:
+                for k in range(n_buckets):
+                    if pending[k] is not None:
+                        pending[k].wait()
+                        pending[k] = None
+                i = last["i"]      # a partially filled last bucket is reduced here
+                if i >= 0 and i % every != every - 1:
+                    sharding.all_reduce_totals(buckets[(i // every) % n_buckets])
+                    last["i"] = -1
+        return step, drain
 
-    for i in range(args.warmup):
-        step(i)
-    drain()
-    barrier()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    step, drain = headline(1)
     with ClockSampler(local_rank) as clocks:
-        barrier()
-        ev[0].record()
-        for i in range(args.steps):
-            step(args.warmup + i)
-        drain()
-        ev[1].record()
-        barrier()
-    total_ms = ev[0].elapsed_time(ev[1])
-    # average launch duration of the kernel over the timed region (launch gaps included): the steps are back to back
-    # on one stream and each step is exactly one launch of the quantize kernel
-    per_launch_ms = [total_ms / args.steps]
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+        total_ms = max_over_ranks(_time_steps(step, args.steps, args.warmup, barrier, drain))
     value = COORDS * world * args.steps / (total_ms * 1e-3)
+    variants = {"collective_every": 1}
+    if world > 1:
+        step4, drain4 = headline(n_sets)
+        ms4 = max_over_ranks(_time_steps(step4, args.steps, args.warmup, barrier, drain4))
+        variants["collective_every_%d" % n_sets] = {"value": COORDS * world * args.steps / (ms4 * 1e-3), "unit": UNIT}
 
-    # end-to-end through the C-ABI host entry point (vbq_quantize_host, what the reference-facing
-    # compress_batch_channel_latents runs for host arrays): HOST pinned buffers in, HOST pinned buffers out, the
-    # upload / kernel / download of row chunks overlapped on three streams, all inside the timed region.
-    h_mu = [b["mu"].cpu().pin_memory() for b in (sets * 2)[:2]]
-    h_sigma = [b["sigma"].cpu().pin_memory() for b in (sets * 2)[:2]]
-    h_q = torch.empty((1, ROWS, C), dtype=torch.int32).pin_memory()
-    h_b = torch.empty((1, ROWS, C), dtype=torch.float32).pin_memory()
-    h_tot = torch.empty((1, 4), dtype=torch.float64).pin_memory()
-    pipe = ops.HostPipeline(C, N_BITS, 1, args.chunk_rows, ops.OUT_QIDX | ops.OUT_BITS | ops.OUT_TOTALS, device=dev)
+    # ---- end to end through the reference-facing call on HOST arrays -------------------------------------------------
+    # ChannelwisePriorCDFQuantizer.compress_batch_channel_latents(batch_means, batch_stds, lambs) on pinned NumPy arrays
+    # (quantizer.py:156-188): the facade feeds the chunked upload / kernel / download pipeline (vbq_quantize_host) and
+    # returns Z_hat_dict, num_bits_dict as host arrays; every byte crosses PCIe inside the timed region.
+    h_in = [(b["mu"].cpu().pin_memory().numpy(), b["sigma"].cpu().pin_memory().numpy()) for b in (sets * 2)[:2]]
+    state = {}
 
     def e2e_step(i):
-        pipe.run(h_mu[i % 2], h_sigma[i % 2], q.all_code_points, q._packed, pen, length, None,
-                 qidx=h_q, bits=h_b, totals=h_tot, flags=args.flags)
-        if world > 1:
-            t_ = h_tot.to(dev)
-            sharding.all_reduce_totals(t_)
-            h_tot.copy_(t_)
-        return float(h_tot[0, 1])
+        Z, B = q.compress_batch_channel_latents(h_in[i % 2][0], h_in[i % 2][1], [LAMB])
+        state["last"] = (Z[LAMB], B[LAMB])
 
     e2e_steps = max(3, min(args.steps, 20))
-    for i in range(2):
-        e2e_step(i)
-    # the pipeline must reproduce the device-resident results exactly
+    for i in range(5):      # warm-up: the facade's pinned output buffers come from PyTorch's caching host allocator
+        e2e_step(i)             # (the last one, i = 4, used input set 0: checked below)
+    # the facade must reproduce the device-resident results exactly: its z_hat is the code point the index names
     step(0)
     drain()
     torch.cuda.synchronize()
-    pipe.run(h_mu[0], h_sigma[0], q.all_code_points, q._packed, pen, length, None, qidx=h_q, bits=h_b, totals=h_tot,
-             flags=args.flags)
-    assert torch.equal(h_q[0], sets[0]["qidx"][0].cpu()) and torch.equal(h_b[0], sets[0]["bits"][0].cpu())
+    zt = q.code_points_by_channel.t().contiguous()
+    want_z = torch.gather(zt, 0, sets[0]["qidx"][0].long()).cpu().numpy()
+    assert np.array_equal(state["last"][0], want_z) and np.array_equal(state["last"][1], sets[0]["bits"][0].cpu().numpy().astype(np.int32))
     barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         e2e_step(i)
     barrier()
-    e2e_s = time.perf_counter() - t0
-    pipe.close()
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = COORDS * world * e2e_steps / float(t.item())
+    e2e_value = COORDS * world * e2e_steps / max_over_ranks(time.perf_counter() - t0)
+    # what the box moves at most: the same bytes per step as bare pinned copies (H2D on one stream, D2H on another)
+    d_a = torch.empty((2, ROWS, C), dtype=torch.float32, device=dev)
+    h_a = torch.empty((2, ROWS, C), dtype=torch.float32).pin_memory()
+    h_b2 = torch.empty((2, ROWS, C), dtype=torch.float32).pin_memory()
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def copy_step(i):
+        with torch.cuda.stream(s1):
+            d_a.copy_(h_a, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_b2.copy_(d_a, non_blocking=True)
+
+    for i in range(2):
+        copy_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        copy_step(i)
+    barrier()
+    ceiling = COORDS * world * e2e_steps / max_over_ranks(time.perf_counter() - t0)
+    del d_a, h_a, h_b2
+
+    # ---- the reference's production mode: corrected code lengths + entropy-model bits (quantizer.py:166-180, :223-228) --
+    extra = {}
+    if not args.headline_only:
+        extra["corrected"] = bench_corrected(q, sets, world, dev, barrier, max_over_ranks)
+        extra["configs"] = bench_configs(prior, q, rank, world, dev, barrier, max_over_ranks)
 
     if rank != 0:
         return
     peaks, peak_kind = measured_peaks()
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")   # dram__bytes_read+write of one ncu --set full capture
+    tp = os.path.join(ROOT, "profiles", "r2_traffic.json")   # dram__bytes_read+write of one ncu --set full capture
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f)["traffic_bytes_per_launch"]
-    kern_ms = float(np.median(per_launch_ms))
-    achieved = COORDS * BYTES_PER_COORD / (kern_ms * 1e-3) / 1e9
+    kern_ms = total_ms / args.steps     # average launch duration over the timed region (launch gaps included): the
+    achieved = COORDS * BYTES_PER_COORD / (kern_ms * 1e-3) / 1e9   # steps are back to back, one launch each
     cpu = None
     if world == 1 and not args.no_cpu:
         b = sets[0]
@@ -423,19 +451,121 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD, "coords_per_step_per_gpu": COORDS, "max_bits_per_coord": N_BITS,
                    "lambdas": [LAMB], "outputs": "sorted quantile index int32 + code length f32 + totals",
                    "l2": "%d rotating input/output sets (%d MB) > 126 MB L2" % (n_sets, n_sets * set_bytes >> 20),
-                   "flags": args.flags, "parallelism": "dp%d, totals (n_lambda,4) f64 all-reduced over NCCL in buckets of %d steps" % (world, n_sets)},
+                   "flags": args.flags, "parallelism": "dp%d, totals (n_lambda,4) f64 all-reduced over NCCL once per call" % world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
-                     "kernel": "vbq_bisect_kernel", "kernel_ms": kern_ms,
+                     "kernel": "vbq_bisect_tma_kernel", "kernel_ms": kern_ms,
                      "algorithmic_bytes_per_launch": COORDS * BYTES_PER_COORD},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 2 * COORDS * 4,
-                "d2h_bytes_per_step": 2 * COORDS * 4 + 32, "steps": e2e_steps,
-                "api": "vbq_quantize_host (pinned host in/out, %d-row chunks, 3 streams)" % args.chunk_rows},
+                "d2h_bytes_per_step": 2 * COORDS * 4, "steps": e2e_steps,
+                "api": "ChannelwisePriorCDFQuantizer.compress_batch_channel_latents on pinned NumPy arrays (z_hat f32 + "
+                       "depth i32 back as NumPy; vbq_quantize_host underneath: 9216-row chunks, 3 streams)",
+                "copy_only_ceiling": ceiling, "frac_of_ceiling": e2e_value / ceiling},
+        "scaling_variants": variants,
         "gpu_launches": args.steps,
         "clocks": clocks.summary(),
     }
+    line.update(extra)
     print(json.dumps(line))
+
+
+def bench_corrected(q0, sets, world, dev, barrier, max_over_ranks):
+    """Same Kodak batch in the mode every reference call runs in after build_entropy_models (quantizer.py:166-180,
+    utils.py:392-396; the path utils.py:542 -> compress -> compress_latents): per-channel corrected code lengths
+    n + R_lambda[c, n], z_hat + corrected length + entropy-model bits out.  Entropy models fitted on the batch itself."""
+    import torch
+    import vbq_b200
+    from vbq_b200 import ops
+    grid = [float(l) for l in 2.0 ** np.linspace(-8, 7, 16)]
+    q = vbq_b200.ChannelwisePriorCDFQuantizer(C, N_BITS, device=dev)
+    q.set_code_points(q0.all_code_points)
+    b = sets[0]
+    logvar = (2.0 * torch.log(b["sigma"])).contiguous()
+    q.build_entropy_models_from_latents(b["mu"], logvar, grid, add_n_smoothing=1.0)
+    out = {}
+    for name, lambs in (("single_lambda", [LAMB]), ("grid16", grid)):
+        def fn(i, lambs=lambs):
+            bb = sets[i % len(sets)]
+            q.quantize(bb["mu"], bb["sigma"], lambs, outputs=ops.OUT_ZHAT | ops.OUT_BITS | ops.OUT_TOTALS, entropy_bits=True)
+        ms = max_over_ranks(_time_steps(fn, 10, 3, barrier))
+        out[name] = {"lambdas": len(lambs), "ms_per_call": ms / 10,
+                     "value": COORDS * len(lambs) * world * 10 / (ms * 1e-3), "unit": "coord-lambdas/s",
+                     "outputs": "z_hat f32 + corrected code length f32 + entropy-model bits f32 + totals"}
+    return out
+
+
+def bench_configs(prior, q, rank, world, dev, barrier, max_over_ranks):
+    """BASELINE.json configs[2..4] at this N, each through vbq_b200.sharding.ShardedQuantizer with ONE all-reduce of the
+    totals per call inside the timed region.  Config 3 and 5 run the per-GPU share of the 8-GPU problem (weak scaling:
+    512 / 32 images per GPU); config 4 is strong-scaled (1 M rows / N per rank)."""
+    import torch
+    import vbq_b200
+    from vbq_b200 import ops, sharding
+    res = {}
+    g = torch.Generator(device=dev)
+    g.manual_seed(77 + rank)
+
+    # configs[2]: 4096 synthetic 512x768 images (32x48 latents x 192), 64-point lambda sweep, totals only
+    imgs = 512
+    rows = imgs * H * W
+    u = torch.rand((rows, C), generator=g, device=dev, dtype=torch.float64) * 0.998 + 0.001
+    mu = prior.inverse_cdf(u).contiguous()
+    del u
+    sigma = torch.exp(0.5 * (torch.randn((rows, C), generator=g, device=dev) * 1.5 - 3.0)).contiguous()
+    sq = sharding.ShardedQuantizer(q)
+    lambs = [float(l) for l in 2.0 ** np.linspace(-8, 7, 64)]
+    ms = max_over_ranks(_time_steps(lambda i: sq.rd_sweep(mu, sigma, lambs), 3, 2, barrier)) / 3
+    res["config3_sweep64"] = {
+        "workload": "%d images/GPU x 32x48x192 latents, 64 lambdas 2^linspace(-8,7,64), totals only" % imgs,
+        "ms_per_call": ms, "value": rows * C * 64 * world / (ms * 1e-3), "unit": "coord-lambdas/s", "scaling": "weak",
+        "hbm_frac_at_8B_per_coord": rows * C * 8 / (ms * 1e-3) / 1e9 / measured_peaks()[0]["hbm_gbs"]}
+    del mu, sigma
+
+    # configs[3]: word embeddings 1M x 300, row-sharded (strong scaling): float32 kernel and the default float64 search
+    V, K = 1_000_000, 300
+    a, b_ = sharding.shard_bounds(V, world, rank)
+    means = torch.randn((b_ - a, K), generator=g, device=dev) * 1.2329 - 0.08
+    stds = torch.exp(torch.randn((b_ - a, K), generator=g, device=dev) * 0.7 + float(np.log(0.04)))
+    cb = vbq_b200.GaussianCodebook(1.2356, 10, device=dev)
+
+    def emb32(i):
+        out = cb.quantize(means, stds, [1.0], outputs=ops.OUT_ZHAT | ops.OUT_TOTALS)
+        sharding.all_reduce_totals(out["totals"])
+
+    def emb64(i):
+        cb.compress_coordinates(means, stds, 1.0, exact=True)
+
+    ms32 = max_over_ranks(_time_steps(emb32, 5, 2, barrier)) / 5
+    ms64 = max_over_ranks(_time_steps(emb64, 3, 1, barrier)) / 3
+    res["config4_embeddings"] = {
+        "workload": "1M x 300 Gaussian posteriors, rows/N per rank, beta = 1, N = 10", "scaling": "strong",
+        "float32_kernel": {"ms_per_call": ms32, "value": V * K / (ms32 * 1e-3), "unit": UNIT,
+                           "api": "GaussianCodebook.quantize (z_hat + totals, one all-reduce per call)"},
+        "float64_default": {"ms_per_call": ms64, "value": V * K / (ms64 * 1e-3), "unit": UNIT,
+                            "api": "GaussianCodebook.compress_coordinates(exact=True), the notebook's arithmetic"}}
+    del means, stds
+
+    # configs[4]: 256 synthetic 2048x2048 images x 320 channels (128x128 latents), max bit depth 16
+    C5, N5, imgs5 = 320, 16, 256 // 8
+    rows5 = imgs5 * 128 * 128
+    prior5 = vbq_b200.BMSHJ2018Prior(C5, device=dev, seed=5)
+    q5 = vbq_b200.ChannelwisePriorCDFQuantizer(C5, N5, device=dev)
+    q5.build_code_points(prior5)
+    u = torch.rand((rows5, C5), generator=g, device=dev, dtype=torch.float64) * 0.998 + 0.001
+    mu5 = prior5.inverse_cdf(u).contiguous()
+    del u
+    sg5 = torch.exp(0.5 * (torch.randn((rows5, C5), generator=g, device=dev) * 1.5 - 3.0)).contiguous()
+    sq5 = sharding.ShardedQuantizer(q5)
+    r5 = {"workload": "%d images/GPU x 128x128x320 latents, N = 16, sorted index + code length + totals" % imgs5,
+          "scaling": "weak"}
+    for name, lamb in (("lambda_0.5", 0.5), ("lambda_2^-8", 2.0 ** -8)):
+        ms = max_over_ranks(_time_steps(lambda i: sq5.quantize(mu5, sg5, [lamb], ops.OUT_QIDX | ops.OUT_BITS), 3, 2,
+                                        barrier)) / 3
+        r5[name] = {"ms_per_call": ms, "value": rows5 * C5 * world / (ms * 1e-3), "unit": UNIT,
+                    "roofline_frac": rows5 * C5 * 16 / (ms * 1e-3) / 1e9 / measured_peaks()[0]["hbm_gbs"]}
+    res["config5_deep"] = r5
+    return res
 
 
 def main():
@@ -448,6 +578,7 @@ def main():
     ap.add_argument("--chunk-rows", type=int, default=9216, help="rows per chunk of the host pipeline (e2e leg)")
     ap.add_argument("--no-reserve", action="store_true", help="multi-GPU: do not leave an SM to the NCCL kernel")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--headline-only", action="store_true", help="skip the `corrected` and `configs` sections")
     ap.add_argument("--graph", action="store_true", help="replay one CUDA graph per step instead of the prebound eager "
                     "call (the eager launches overlap through programmatic dependent launch and measure faster)")
     args = ap.parse_args()

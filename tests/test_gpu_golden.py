@@ -102,11 +102,31 @@ def test_entropy_model_fit_and_compress_latents(name):
     q.build_entropy_models(X, VAE(), lambs, add_n_smoothing=1)
     assert q.lambs == sorted(lambs)
     total = mism = 0
+    n_sym = g["means"].size // g["means"].shape[-1]           # symbols per channel
+
+    def counts_of(table):   # -log2((count + 1) / (n_sym + bins)) -> count (add_n_smoothing = 1)
+        return np.rint(np.exp2(-table.astype(np.float64)) * (n_sym + table.shape[1])) - 1
+
+    moved = 0
     for i, l in enumerate(lambs):
         assert q.raw_code_length_entropy_models[l].dtype == np.float32
-        # identical histograms <=> identical tables; allow the handful of sigma-ulp ties to move single counts
-        assert np.allclose(q.raw_code_length_entropy_models[l], g["rcl_%d" % i], rtol=0, atol=0.05)
-        assert np.allclose(q.entropy_models[l], g["em_%d" % i], rtol=0, atol=1.01)
+        # identical histograms <=> identical tables; COUNT the symbols that the sigma-ulp ties moved to another bin
+        for ours, ref in ((q.raw_code_length_entropy_models[l], g["rcl_%d" % i]), (q.entropy_models[l], g["em_%d" % i])):
+            co, cr = counts_of(ours), counts_of(ref)
+            assert np.all(co.sum(axis=1) == n_sym) and np.all(cr.sum(axis=1) == n_sym)
+            d = int(np.abs(co - cr).sum()) // 2
+            moved += d
+            if d == 0:
+                assert np.array_equal(ours, ref)
+    print("entropy-model fit: %d of %d symbols counted in another bin than the reference's" % (moved, 2 * len(lambs) * g["means"].size))
+    assert moved <= max(2, 2 * len(lambs) * g["means"].size // 50000)
+    # fed the reference's own float32 sigma = exp(logvar) ** 0.5 (quantizer.py:93) the tables are the reference's, bit for bit
+    q_s = make_quantizer(g)
+    stds = np.exp(g["logvars"].astype(np.float32)) ** np.float32(0.5)
+    q_s.build_entropy_models_from_latents(g["means"], None, lambs, add_n_smoothing=1, posterior_stds=stds)
+    for i, l in enumerate(lambs):
+        assert np.array_equal(q_s.raw_code_length_entropy_models[l], g["rcl_%d" % i])
+        assert np.array_equal(q_s.entropy_models[l], g["em_%d" % i])
     # with the reference's fitted tables installed, compress() must reproduce the reference's outputs
     q.raw_code_length_entropy_models = {l: g["rcl_%d" % i] for i, l in enumerate(lambs)}
     q.entropy_models = {l: g["em_%d" % i] for i, l in enumerate(lambs)}

@@ -138,10 +138,16 @@ def quantize_into(mu, sigma, table, packed, penalty, length, entropy_model, max_
         if workspace is None:
             raise ValueError("vbq_b200: totals need a workspace (see quantize_workspace)")
         ws_bytes = workspace.numel() * workspace.element_size()
-    st = lib.vbq_quantize_hp(_ptr(mu), _ptr(sigma), rows, C, _ptr(table), _ptr(packed), max_bits,
-                             _ptr(penalty), _host_penalty_ptr(penalty), _ptr(length), n_lambda, pen_channels,
-                             _ptr(entropy_model), _ptr(zhat), _ptr(qidx), _ptr(level), _ptr(bits), _ptr(em_bits),
-                             _ptr(totals), _ptr(workspace), ws_bytes, _table_flags(packed, flags), _stream(mu.device))
+    for name, t in (("sigma", sigma), ("table", table), ("packed", packed), ("penalty", penalty), ("length", length),
+                    ("entropy_model", entropy_model), ("zhat", zhat), ("qidx", qidx), ("level", level), ("bits", bits),
+                    ("em_bits", em_bits), ("totals", totals), ("workspace", workspace)):
+        if t is not None and t.device != mu.device:
+            raise ValueError("vbq_b200: `%s` lives on %s but `mu` on %s" % (name, t.device, mu.device))
+    with torch.cuda.device(mu.device):   # the library launches on the CURRENT device
+        st = lib.vbq_quantize_hp(_ptr(mu), _ptr(sigma), rows, C, _ptr(table), _ptr(packed), max_bits,
+                                 _ptr(penalty), _host_penalty_ptr(penalty), _ptr(length), n_lambda, pen_channels,
+                                 _ptr(entropy_model), _ptr(zhat), _ptr(qidx), _ptr(level), _ptr(bits), _ptr(em_bits),
+                                 _ptr(totals), _ptr(workspace), ws_bytes, _table_flags(packed, flags), _stream(mu.device))
     _lib.check(st, "vbq_quantize_hp")
 
 
@@ -185,7 +191,11 @@ class QuantizePlan:
             self._graph = g
 
     def _call(self):
-        st = self._fn(*self._cargs, _stream(self._device))
+        if torch.cuda.current_device() != self._device.index:
+            with torch.cuda.device(self._device):
+                st = self._fn(*self._cargs, _stream(self._device))
+        else:
+            st = self._fn(*self._cargs, _stream(self._device))
         if st != _lib.OK:
             _lib.check(st, "vbq_quantize_hp")
 

@@ -280,11 +280,11 @@ class ChannelwisePriorCDFQuantizer:
         posterior_means, posterior_logvars = vae.encode(X)
         return self.build_entropy_models_from_latents(posterior_means, posterior_logvars, lambs, add_n_smoothing)
 
-    def _histograms(self, m, lv, lambs, what, reduce_fn=None):
+    def _histograms(self, m, lv, lambs, what, reduce_fn=None, logvar=True):
         """Per-(lambda, channel) counts of the chosen depth ('level', N+1 bins) or sorted index ('qidx', Q bins)."""
         C, N, Q = self.num_channels, self.max_bits_per_coord, self.quantization_levels
         nbins = N + 1 if what == 'level' else Q
-        out = self.quantize(m, lv, lambs, logvar=True, outputs=ops.OUT_LEVEL if what == 'level' else ops.OUT_QIDX)
+        out = self.quantize(m, lv, lambs, logvar=logvar, outputs=ops.OUT_LEVEL if what == 'level' else ops.OUT_QIDX)
         sym = out[what]                                                      # (Lambda, rows, C) int32
         ch = torch.arange(C, device=self.device, dtype=torch.int64)
         counts = []
@@ -300,17 +300,21 @@ class ChannelwisePriorCDFQuantizer:
         return counts.cpu().numpy()
 
     def build_entropy_models_from_latents(self, posterior_means, posterior_logvars, lambs, add_n_smoothing,
-                                          reduce_fn=None):
+                                          reduce_fn=None, posterior_stds=None):
         """Two-pass fit of quantizer.py:82-150 on given latents.  ``reduce_fn`` (optional) all-reduces the int64
-        count tensors across data-parallel ranks (vbq_b200.sharding.all_reduce_counts)."""
-        C = int(posterior_logvars.shape[-1])
+        count tensors across data-parallel ranks (vbq_b200.sharding.all_reduce_counts).  ``posterior_stds`` (optional)
+        replaces ``posterior_logvars`` by ready-made standard deviations, e.g. the reference's own float32
+        `exp(logvar) ** 0.5` (quantizer.py:93), with which the fitted tables are bit-identical to the reference's."""
+        logvar = posterior_stds is None
+        scales = posterior_logvars if logvar else posterior_stds
+        C = int(scales.shape[-1])
         assert C == self.num_channels
-        m, lv = self._prep(posterior_means, posterior_logvars)
+        m, lv = self._prep(posterior_means, scales)
         float_type = self.float_type
 
         self.raw_code_length_entropy_models = None
         self._cache = {}
-        counts = self._histograms(m, lv, lambs, 'level', reduce_fn)
+        counts = self._histograms(m, lv, lambs, 'level', reduce_fn, logvar)
         raw_code_length_entropy_models = dict()
         for i, lamb in enumerate(lambs):
             c = counts[i].astype(float_type)
@@ -321,7 +325,7 @@ class ChannelwisePriorCDFQuantizer:
 
         # second pass with the corrected code lengths n + R_lambda[c, n]
         self._cache = {}
-        counts = self._histograms(m, lv, lambs, 'qidx', reduce_fn)
+        counts = self._histograms(m, lv, lambs, 'qidx', reduce_fn, logvar)
         entropy_models = dict()
         for i, lamb in enumerate(lambs):
             c = counts[i].astype(float_type)

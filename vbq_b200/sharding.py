@@ -29,14 +29,16 @@ def shard_leading_axis(x, world_size=None, rank=None):
     return x[a:b]
 
 
-def all_reduce_totals(totals, group=None):
-    """Sum the per-shard (n_lambda, 4) float64 totals over all ranks, in place; returns ``totals``.
+def all_reduce_totals(totals, group=None, async_op=False):
+    """Sum the per-shard (n_lambda, 4) float64 totals over all ranks, in place; returns ``totals`` (or, with
+    ``async_op``, the work handle to wait on — None when there is nothing to reduce).
     Columns: sum of raw depth n, sum of code length, sum of entropy-model bits, sum (z_hat-mu)^2/(2 sigma^2)."""
     if totals.dtype != torch.float64:
         raise TypeError("totals must be float64")
+    work = None
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=group)
-    return totals
+        work = dist.all_reduce(totals, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    return work if async_op else totals
 
 
 def all_reduce_counts(counts, group=None):
@@ -63,6 +65,16 @@ class ShardedQuantizer:
         out = self.quantizer.quantize(local_means, local_scales, lambs, logvar=logvar, outputs=ops.OUT_TOTALS,
                                       flags=flags, entropy_bits=entropy_bits)
         return all_reduce_totals(out['totals'], self.group)
+
+    def quantize(self, local_means, local_scales, lambs, outputs, logvar=False, entropy_bits=False, flags=0):
+        """Full outputs for this rank's shard (they stay on the rank) plus the GLOBAL totals: one all-reduce per call."""
+        from . import ops
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            flags |= ops.FLAG_RESERVE_SM
+        out = self.quantizer.quantize(local_means, local_scales, lambs, logvar=logvar, outputs=outputs | ops.OUT_TOTALS,
+                                      flags=flags, entropy_bits=entropy_bits)
+        all_reduce_totals(out['totals'], self.group)
+        return out
 
     def build_entropy_models_from_latents(self, local_means, local_logvars, lambs, add_n_smoothing):
         return self.quantizer.build_entropy_models_from_latents(

@@ -64,7 +64,7 @@ class GaussianCodebook:
         N = self.max_codepoint_length
         per_level = self._level_lengths(self.lengths if bitlengths is None else bitlengths).astype(np.float32)
         pen = np.stack([np.float32(b) * per_level for b in betas])[:, None, :]
-        pen = torch.from_numpy(np.ascontiguousarray(pen, dtype=np.float32)).to(self.device)
+        pen = ops.with_host_copy(pen, self.device)   # channel-independent: launch constants of the TMA kernel
         # the notebook's default lengths are the bit depths themselves: no length table, which lets vbq_quantize use
         # the certified-bisection kernels (raw code lengths); custom bitlengths go through the length-table path
         length = None
