@@ -14,7 +14,7 @@
  *                  — quantizer.py:30-36 `all_code_points`; the notebook's `codepoints` (ipynb:383-390) is one row
  *   packed table   ceil(C/16) groups x 2069 entries x 16 channels, the shared-memory image of a 16-channel group:
  *                  bit depths 0..10, each stored as [pad, 2^n points, pad] so bracket ends need no clamping;
- *                  followed by ceil(C/16) "walk trees" of 40960 floats (the same code points in heap order, scaled by
+ *                  followed by ceil(C/16) "walk trees" of 40992 floats (the same code points in heap order, scaled by
  *                  2^24, bit depths 1..7 twice: the shared-memory image of vbq_bisect_tma_kernel); made by
  *                  vbq_pack_code_points, vbq_packed_table_floats(C, N) floats in all
  *   prior params   (C, 43) float32: for layer k=0..3: matrix (d_{k+1} x d_k row-major), bias (d_{k+1}),

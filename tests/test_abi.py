@@ -33,8 +33,8 @@ def test_version_and_status_strings():
     assert lib.vbq_version() == 100
     assert lib.vbq_status_string(0) == b"ok"
     assert lib.vbq_status_string(3) == b"bad max_bits_per_coord"
-    assert lib.vbq_packed_table_floats(192, 10) == 12 * (2069 * 16 + 40960)
-    assert lib.vbq_packed_table_floats(1, 0) == 2069 * 16 + 40960
+    assert lib.vbq_packed_table_floats(192, 10) == 12 * (2069 * 16 + 40992)
+    assert lib.vbq_packed_table_floats(1, 0) == 2069 * 16 + 40992
     assert lib.vbq_packed_table_floats(0, 10) == -1 and lib.vbq_packed_table_floats(4, 21) == -1
     assert lib.vbq_quantize_workspace_bytes(1) == 256 + 1024 * 4 * 8
     assert lib.vbq_quantize_workspace_bytes(0) == -1
@@ -73,7 +73,7 @@ def test_no_cpu_fallback():
     import vbq_b200
     from vbq_b200 import ops
     with pytest.raises(RuntimeError, match="CUDA tensor"):
-        ops.quantize(torch.zeros(4, 2), torch.ones(4, 2), torch.zeros(2, 7), torch.zeros(2069 * 16 + 40960),
+        ops.quantize(torch.zeros(4, 2), torch.ones(4, 2), torch.zeros(2, 7), torch.zeros(2069 * 16 + 40992),
                      torch.zeros(1, 1, 3), None, None, 2, ops.OUT_ZHAT, 0)
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         ops.learned_cdf(torch.zeros(2, 43), torch.zeros(3, 2))

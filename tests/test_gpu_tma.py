@@ -1,0 +1,100 @@
+"""The TMA pipeline kernels (csrc/quantize_tma.cuh) against the literal reference walk (VBQ_FLAG_REFERENCE_WALK: both
+bracket ends of every depth, IEEE float32 scores, first maximum in the reference's candidate order — quantizer.py:156-188,
+utils.py:392-415) and against the cp.async bisection kernel, on inputs with near-ties in bulk: a third of the coordinates
+sit exactly on code points, rows far outside the table, ragged row counts and channel counts, N < 10, early exit on/off.
+Outputs must be identical; the totals identical between repeated runs and within 2e-7 of the other kernels' (the
+distortion total is an exact sum of terms rounded to 2^-24)."""
+import numpy as np
+import pytest
+import torch
+
+import vbq_b200
+from vbq_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DT = {"zhat": torch.float32, "qidx": torch.int32, "level": torch.int32, "bits": torch.float32, "em_bits": torch.float32}
+
+
+def _case(rows, C, N, seed):
+    dev = torch.device("cuda", 0)
+    pr = vbq_b200.BMSHJ2018Prior(C, device=dev, seed=seed)
+    q = vbq_b200.ChannelwisePriorCDFQuantizer(C, N, device=dev)
+    q.build_code_points(pr)
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    u = torch.rand((rows, C), generator=g, device=dev, dtype=torch.float64) * 0.9998 + 0.0001
+    m = pr.inverse_cdf(u).contiguous()
+    tab = q.all_code_points
+    idx = torch.randint(0, tab.shape[1], (rows, C), generator=g, device=dev)
+    onpt = tab.t()[idx, torch.arange(C, device=dev)[None, :].expand(rows, C)]
+    m = torch.where(torch.rand((rows, C), generator=g, device=dev) < 0.33, onpt, m).contiguous()
+    if rows > 8:
+        m[0] = 1e4
+        m[1] = -1e4
+        m[2] = tab[:, -1] * 1.0000001 + 1e-3          # just above the highest code point of the deepest level
+        m[3] = tab[:, tab.shape[1] // 2]
+    s = torch.exp(0.5 * (torch.randn((rows, C), generator=g, device=dev) * 1.5 - 3.0)).contiguous()
+    return q, m, s
+
+
+def _run(q, m, s, pen, length, em, flags, outs, N):
+    L, (rows, C) = pen.shape[0], m.shape
+    o = {k: torch.full((L, rows, C), -7, dtype=DT[k], device=m.device) for k in outs}
+    tot = torch.zeros((L, 4), dtype=torch.float64, device=m.device)
+    ops.quantize_into(m, s, q.all_code_points, q._packed, pen, length, em, N, totals=tot,
+                      workspace=ops.quantize_workspace(L, m.device), flags=flags, **o)
+    torch.cuda.synchronize()
+    return o, tot
+
+
+def _same(a, b):
+    return all(torch.equal(a[k], b[k]) for k in a)
+
+
+def _close(t, r):
+    return float(((t - r).abs() / r.abs().clamp_min(1e-300)).max()) <= 2e-7
+
+
+@pytest.mark.parametrize("rows,C,N,lambs", [(1, 16, 10, [0.5]), (17, 20, 10, [0.5]), (1000, 36, 10, [0.01, 2.0]),
+                                            (4099, 192, 10, [0.5, 8.0, 0.0]), (677, 48, 6, [0.3]), (333, 12, 0, [1.0]),
+                                            (30000, 64, 10, [4.0])])
+def test_raw_lengths_tma_equals_reference_walk(rows, C, N, lambs):
+    q, m, s = _case(rows, C, N, rows + C)
+    pen, length = q._length_tables(lambs)            # carries its host copy: the TMA kernel applies
+    for outs in (("qidx", "bits"), ("zhat", "level"), ("zhat",), ("qidx",), ()):
+        for fl in (0, ops.FLAG_NO_PRUNE):
+            f = fl | ops.FLAG_NO_SWEEP
+            ref, tr = _run(q, m, s, pen, length, None, f | ops.FLAG_REFERENCE_WALK, outs, N)
+            old, to = _run(q, m, s, pen, length, None, f | ops.FLAG_NO_TMA, outs, N)
+            new, tn = _run(q, m, s, pen, length, None, f, outs, N)
+            new2, tn2 = _run(q, m, s, pen, length, None, f, outs, N)
+            assert _same(ref, new) and _same(old, new), (outs, fl)
+            assert torch.equal(tn, tn2) and _close(tn, tr) and _close(to, tr)
+            assert torch.equal(tn[:, 0], tr[:, 0])                       # depth sums are integers: exact
+
+
+@pytest.mark.parametrize("rows,C,lambs", [(1, 16, [0.5]), (37, 20, [0.3]), (1000, 36, [0.01, 2.0]),
+                                          (4099, 192, [0.5, 8.0, 0.0]), (20000, 64, [0.05])])
+def test_arbitrary_penalties_tma_equals_reference_walk(rows, C, lambs):
+    """Corrected code lengths n + R_lambda[c, n] with a non-monotone R, and the fused entropy-model gather."""
+    N = 10
+    q, m, s = _case(rows, C, N, 7 * rows + C)
+    rng = np.random.default_rng(rows)
+    L = len(lambs)
+    R = rng.gamma(2.0, 2.0, size=(L, C, N + 1)).astype(np.float32)
+    length = (np.arange(N + 1, dtype=np.float32)[None, None, :] + R).astype(np.float32)
+    pen = ops.with_host_copy(np.asarray(lambs, dtype=np.float32)[:, None, None] * length, m.device)
+    len_t = torch.from_numpy(length).to(m.device)
+    em = torch.from_numpy(rng.gamma(2.0, 3.0, size=(L, C, 2 ** (N + 1) - 1)).astype(np.float32)).to(m.device)
+    for outs, em_ in ((("zhat", "bits", "em_bits"), em), (("zhat", "bits"), em), (("zhat", "bits"), None),
+                      (("qidx",), None), ((), em), ((), None)):
+        f = ops.FLAG_NO_SWEEP
+        ref, tr = _run(q, m, s, pen, len_t, em_, f | ops.FLAG_REFERENCE_WALK, outs, N)
+        new, tn = _run(q, m, s, pen, len_t, em_, f, outs, N)
+        new2, tn2 = _run(q, m, s, pen, len_t, em_, f, outs, N)
+        assert _same(ref, new), outs
+        assert torch.equal(tn, tn2) and _close(tn, tr)
+    # several lambdas in one call (no NO_SWEEP) with the gather: per-lambda launches of the same kernel
+    ref, tr = _run(q, m, s, pen, len_t, em, ops.FLAG_REFERENCE_WALK, ("zhat", "bits", "em_bits"), N)
+    new, tn = _run(q, m, s, pen, len_t, em, 0, ("zhat", "bits", "em_bits"), N)
+    assert _same(ref, new) and _close(tn, tr)

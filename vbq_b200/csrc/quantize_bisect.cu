@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
     float *wStage = sStage + warp * (kStages * kTileFloats);
     const float *myStage = wStage + par * VBQ_GROUP + col;   // + slot*kTileFloats + arr*64 + u*32
 
-    unsigned long long acc_dist = 0;   // distortion terms in units of 2^-24: an integer sum does not depend on which warp
-                                       // claimed which tile
+    Acc128 acc_dist = {0, 0};   // distortion terms in units of 2^-24: an integer sum does not depend on which warp claimed
+                                // which tile
     int acc_level = 0;   // < 2^31: at most 2^29 coordinates per launch, depth <= 10
     pdl_wait();   // launched with programmatic stream serialization: nothing global is touched before this point
 #ifdef VBQ_TRACE
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
                 float dsum = dist[0];
 #pragma unroll
                 for (int u = 1; u < U; ++u) dsum += dist[u];
-                acc_dist += __float2ull_rn(dsum * 16777216.0f);
+                acc_dist.add_q24(dsum);
             }
         };
 
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
 #endif
     if (TOTALS) {
         // raw-length mode: the code length of depth n is n itself; no entropy model on this path
-        double v[VBQ_TOTALS] = {(double)acc_level, (double)acc_level, 0.0, (double)acc_dist * (1.0 / 16777216.0)};
+        double v[VBQ_TOTALS] = {(double)acc_level, (double)acc_level, 0.0, acc_dist.value()};
         finish_totals<kThreads>(a, lam, v, sRed, &sLast);
     }
 }

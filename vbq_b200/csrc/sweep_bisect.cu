@@ -252,10 +252,10 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_sweep_kernel(const QAr
                     }
                 }
             }
-            if (TOTALS && lb + lane < L) {   // integers (distortion in units of 2^-24): the order of the tiles, which
+            if (TOTALS && lb + lane < L) {   // integers (distortion in units of 2^-16): the order of the tiles, which
                 long long *wAccI = reinterpret_cast<long long *>(wAcc);   // depends on the claims, does not matter
                 wAccI[(lb + lane) * 2 + 0] += my_level;
-                wAccI[(lb + lane) * 2 + 1] += (long long)__float2ull_rn(my_dist * 16777216.0f);
+                wAccI[(lb + lane) * 2 + 1] += (long long)__float2ull_rn(my_dist * 65536.0f);   // 64-coordinate sums: exact to 2^-17
             }
             }
 
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_sweep_kernel(const QAr
         for (int k = threadIdx.x; k < L * 2; k += kThreads) {
             long long si = 0;
             for (int w = 0; w < kWarps; ++w) si += reinterpret_cast<const long long *>(sAcc)[(size_t)w * L * 2 + k];
-            const double s = (k & 1) ? (double)si * (1.0 / 16777216.0) : (double)si;
+            const double s = (k & 1) ? (double)si * (1.0 / 65536.0) : (double)si;
             const int lam = k >> 1;
             double *part = a.partials + ((size_t)lam * kMaxGrid + blockIdx.x) * VBQ_TOTALS;
             if (k & 1) {

@@ -49,33 +49,42 @@ def _need_cuda(name, t, dtype, ndim=None):
         raise ValueError("vbq_b200: `%s` must be %d-D, got shape %s" % (name, ndim, tuple(t.shape)))
 
 
+_HOST_COPIES = {}     # device pointer of a penalty table -> its host original (dropped when the device tensor dies)
+_STABLE_TABLES = set()    # device pointers of packed tables that are known to be complete (see stable_packed)
+
+
 def with_host_copy(penalty_np, device):
     """Device tensor of a host-made penalty table that remembers its host original (float32, C-contiguous).  The
-    search kernels take channel-independent penalties of a single lambda as launch constants when the host copy is
-    available (vbq_quantize_hp); the device tensor alone works too."""
+    search kernels take the penalties of the TMA kernels from the host copy (launch constants / validation,
+    vbq_quantize_hp); the device tensor alone works too (other kernels).  The association is by device address, so it
+    survives the re-wrapping of tensors by torch.library."""
+    import weakref
     import numpy as np
     host = np.ascontiguousarray(penalty_np, dtype=np.float32)
     t = torch.from_numpy(host).to(device)
-    t._vbq_host = host
+    key = (t.data_ptr(), tuple(t.shape))
+    _HOST_COPIES[key] = host
+    weakref.finalize(t, _HOST_COPIES.pop, key, None)
     return t
 
 
 def _host_penalty_ptr(penalty):
-    host = getattr(penalty, "_vbq_host", None)
-    if host is None or tuple(host.shape) != tuple(penalty.shape):
-        return None
-    return host.ctypes.data
+    host = _HOST_COPIES.get((penalty.data_ptr(), tuple(penalty.shape)))
+    return None if host is None else host.ctypes.data
 
 
 def stable_packed(packed):
     """Mark a packed table as complete: the caller has synchronized since vbq_pack_code_points wrote it, so the search
     kernels may read it before earlier kernels of the stream have finished (VBQ_FLAG_TABLE_STABLE).  Returns `packed`."""
-    packed._vbq_stable = True
+    import weakref
+    key = packed.data_ptr()
+    _STABLE_TABLES.add(key)
+    weakref.finalize(packed, _STABLE_TABLES.discard, key)
     return packed
 
 
 def _table_flags(packed, flags):
-    return flags | FLAG_TABLE_STABLE if getattr(packed, "_vbq_stable", False) else flags
+    return flags | FLAG_TABLE_STABLE if packed.data_ptr() in _STABLE_TABLES else flags
 
 
 def search_flags(lambs, flags=0):
