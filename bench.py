@@ -279,8 +279,10 @@ def _time_steps(fn, steps, warmup, barrier, finish=None):
     barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     ev[0].record()
+    t0 = time.perf_counter()
     for i in range(steps):
         fn(warmup + i)
+    _time_steps.host_issue_us = 1e6 * (time.perf_counter() - t0) / max(steps, 1)   # host time to ENQUEUE one step
     if finish:
         finish()
     ev[1].record()
@@ -360,15 +362,58 @@ def run_ours(args, rank, world, local_rank):
                     last["i"] = -1
         return step, drain
 
-    step, drain = headline(1)
+    # N > 1, headline: NO collective launch at all — while call i runs, an idle lane of its kernel writes the totals of call
+    # i-1 into every rank's inbox over NVLink and collects (waits for + adds in rank order) the all-reduced totals of call
+    # i-3 (sharding.PeerTotals / vbq_quantize_peer): one exchange per call, hidden behind the search, no stream operation
+    # between the kernels, all 148 SMs.  The last calls of a run are flushed by the one-CTA push / collect kernels.
+    def headline_peer():
+        flags = args.flags & ~ops.FLAG_RESERVE_SM
+        peer = sharding.PeerTotals(n_lambda_max=1)
+        local = [torch.zeros((1, 4), dtype=torch.float64, device=dev) for _ in sets]
+        plans = [ops.QuantizePlan(b["mu"], b["sigma"], q.all_code_points, q._packed, pen, length, None, N_BITS,
+                                  qidx=b["qidx"], bits=b["bits"], totals=local[s_], flags=flags, peer=peer)
+                 for s_, b in enumerate(sets)]
+        glob = [torch.zeros((1, 4), dtype=torch.float64, device=dev) for _ in range(8)]
+        calls = []          # (sequence number, buffer set) of the calls of this run
+
+        def step(i):
+            calls.append((peer.next_seq(), i % n_sets))
+            k = len(calls) - 1
+            push = calls[k - 1] if k >= 1 else None           # deliver the previous call's totals (n_sets >= 3: its buffer is intact)
+            coll = calls[k - 3] if k >= 3 else None           # collect the call three steps back
+            plans[i % n_sets].run_peer(push[0] if push else 0, local[push[1]] if push else None,
+                                       coll[0] if coll else 0, glob[(k - 3) % 8] if coll else None)
+
+        def drain():
+            n = len(calls)
+            if n:
+                peer.push(calls[n - 1][0], local[calls[n - 1][1]])
+                for k in range(max(0, n - 3), n):
+                    peer.collect(calls[k][0], 1, glob[k % 8])
+            del calls[:]
+        return step, drain, peer, glob, local
+
+    variants = {}
+    if world > 1:
+        step, drain, peer, glob, local = headline_peer()
+        variants["headline"] = "peer inboxes over NVLink: call i delivers the totals of call i-1 and collects those of call i-3 while it runs"
+    else:
+        step, drain = headline(1)
     with ClockSampler(local_rank) as clocks:
         total_ms = max_over_ranks(_time_steps(step, args.steps, args.warmup, barrier, drain))
     value = COORDS * world * args.steps / (total_ms * 1e-3)
-    variants = {"collective_every": 1}
+    host_issue_us = _time_steps.host_issue_us
     if world > 1:
-        step4, drain4 = headline(n_sets)
-        ms4 = max_over_ranks(_time_steps(step4, args.steps, args.warmup, barrier, drain4))
-        variants["collective_every_%d" % n_sets] = {"value": COORDS * world * args.steps / (ms4 * 1e-3), "unit": UNIT}
+        # the exchanged totals are the NCCL all-reduce of the local ones (last call of the timed region)
+        torch.cuda.synchronize()
+        last_k = (args.warmup + args.steps - 1)
+        want = sharding.all_reduce_totals(local[last_k % n_sets].clone())
+        got = glob[(args.steps - 1) % 8]
+        assert torch.allclose(got, want, rtol=1e-12), (got, want)
+        for every in (1, n_sets):       # for comparison: the same steps with NCCL all-reduces (147 CTAs + 1 SM for NCCL)
+            stepn, drainn = headline(every)
+            msn = max_over_ranks(_time_steps(stepn, args.steps, args.warmup, barrier, drainn))
+            variants["nccl_collective_every_%d" % every] = {"value": COORDS * world * args.steps / (msn * 1e-3), "unit": UNIT}
 
     # ---- end to end through the reference-facing call on HOST arrays -------------------------------------------------
     # ChannelwisePriorCDFQuantizer.compress_batch_channel_latents(batch_means, batch_stds, lambs) on pinned NumPy arrays
@@ -451,7 +496,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD, "coords_per_step_per_gpu": COORDS, "max_bits_per_coord": N_BITS,
                    "lambdas": [LAMB], "outputs": "sorted quantile index int32 + code length f32 + totals",
                    "l2": "%d rotating input/output sets (%d MB) > 126 MB L2" % (n_sets, n_sets * set_bytes >> 20),
-                   "flags": args.flags, "parallelism": "dp%d, totals (n_lambda,4) f64 all-reduced over NCCL once per call" % world},
+                   "flags": args.flags, "parallelism": "dp%d, totals (n_lambda,4) f64 exchanged once per call (N > 1: peer inboxes over NVLink, written and collected by the search kernel)" % world},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
                      "kernel": "vbq_bisect_tma_kernel", "kernel_ms": kern_ms,
@@ -463,7 +508,7 @@ def run_ours(args, rank, world, local_rank):
                        "depth i32 back as NumPy; vbq_quantize_host underneath: 9216-row chunks, 3 streams)",
                 "copy_only_ceiling": ceiling, "frac_of_ceiling": e2e_value / ceiling},
         "scaling_variants": variants,
-        "gpu_launches": args.steps,
+        "gpu_launches": args.steps, "host_issue_us_per_step": host_issue_us,
         "clocks": clocks.summary(),
     }
     line.update(extra)

@@ -143,6 +143,37 @@ int vbq_quantize_hp(const float *d_mu, const float *d_sigma, long long rows, int
                     double *d_totals, void *d_workspace, long long workspace_bytes,
                     unsigned flags, void *stream);
 
+/* ---- the exchange step of the data-parallel path (the sums are consumed by utils.py:546-553) ------------ */
+
+/* One context per rank (one process per GPU).  It owns this rank's INBOX in device memory; the 64-byte handle of
+ * vbq_peer_ctx_handle travels to the other ranks of the node by any means (e.g. torch.distributed.all_gather), and
+ * vbq_peer_ctx_connect(handles = world x 64 bytes, in rank order) maps their inboxes (cudaIpc, NVLink peer access). */
+typedef struct vbq_peer_ctx vbq_peer_ctx;
+int vbq_peer_ctx_create(int rank, int world, int n_lambda_max, vbq_peer_ctx **out);
+int vbq_peer_ctx_handle(vbq_peer_ctx *ctx, unsigned char *handle64);
+int vbq_peer_ctx_connect(vbq_peer_ctx *ctx, const unsigned char *handles);
+int vbq_peer_ctx_destroy(vbq_peer_ctx *ctx);
+
+/* The sums of the call with sequence number `seq` (>= 1, chosen by the caller: the same on every rank for the same call,
+ * increasing by one per call) are DELIVERED by writing them into every rank's inbox (peer stores over NVLink + a
+ * system-scope release of the sequence number) and COLLECTED by waiting, on the device, for every rank's entry and adding
+ * the entries in rank order (deterministic) into d_totals (n_lambda, VBQ_TOTALS).  At most 8 calls may be delivered but
+ * not yet collected.  vbq_peer_push / vbq_peer_collect are one-CTA kernels.  vbq_quantize_peer is vbq_quantize_hp that
+ * also delivers the COMPLETED totals of an earlier call (`d_push_totals`, sequence number push_seq; 0 / NULL = none) and
+ * collects a still earlier one (collect_seq -> d_collected; 0 / NULL = none): with n_lambda == 1 an idle lane of the
+ * search kernel does both while the search runs, so a sequence of calls exchanges its totals once per call without any
+ * other stream operation and without a collective library. */
+int vbq_peer_push(vbq_peer_ctx *ctx, unsigned long long seq, int n_lambda, const double *d_totals, void *stream);
+int vbq_peer_collect(vbq_peer_ctx *ctx, unsigned long long seq, int n_lambda, double *d_totals, void *stream);
+int vbq_quantize_peer(const float *d_mu, const float *d_sigma, long long rows, int C,
+                      const float *d_table, const float *d_packed, int N,
+                      const float *d_penalty, const float *h_penalty, const float *d_length, int n_lambda,
+                      int pen_channels, const float *d_entropy_model,
+                      float *d_zhat, int *d_qidx, int *d_level, float *d_bits, float *d_em_bits,
+                      double *d_totals, void *d_workspace, long long workspace_bytes,
+                      unsigned flags, void *stream, vbq_peer_ctx *peer, unsigned long long push_seq,
+                      const double *d_push_totals, unsigned long long collect_seq, double *d_collected);
+
 /* ---- the hot path for host-resident latents ---------------------------------------------------------------- */
 
 /* output selection bits of vbq_host_ctx_create */

@@ -56,9 +56,46 @@ def main():
     for l in lambs:
         assert np.array_equal(rcl_s[l], q.raw_code_length_entropy_models[l])
         assert np.array_equal(em_s[l], q.entropy_models[l])
+    # peer totals: the search kernel's last CTA delivers the sums to every rank's inbox (no NCCL launch); the collected
+    # sum must equal the NCCL all-reduce and, for every rank, be the same bits (rank-ordered addition)
+    peer = sharding.PeerTotals(n_lambda_max=len(lambs))
+    q.raw_code_length_entropy_models, q.entropy_models = None, None
+    q._cache = {}
+    m_loc, s_loc = mu[a:b].reshape(-1, C).contiguous(), torch.exp(0.5 * logvar[a:b]).reshape(-1, C).contiguous()
+    for lam_list in ([0.5], lambs):
+        L = len(lam_list)
+        pen, length = q._length_tables(lam_list)
+        loc_tot = torch.zeros((L, 4), dtype=torch.float64, device=dev)
+        qidx = torch.empty((L, m_loc.shape[0], C), dtype=torch.int32, device=dev)
+        bits = torch.empty((L, m_loc.shape[0], C), dtype=torch.float32, device=dev)
+        plan = ops.QuantizePlan(m_loc, s_loc, q.all_code_points, q._packed, pen, length, None, N, qidx=qidx, bits=bits,
+                                totals=loc_tot, flags=ops.search_flags(lam_list), peer=peer)
+        got = [torch.zeros((L, 4), dtype=torch.float64, device=dev) for _ in range(12)]
+        seqs = [peer.next_seq() for _ in range(12)]
+        for i in range(12):            # more calls than inbox slots; call i delivers call i-1 and collects call i-3 ...
+            if i % 2:
+                plan.run_peer(seqs[i - 1], loc_tot, seqs[i - 3] if i >= 3 else 0, got[i - 3] if i >= 3 else None)
+            else:                      # ... or the stand-alone kernels do
+                if i >= 1:
+                    peer.push(seqs[i - 1], loc_tot)
+                if i >= 3:
+                    peer.collect(seqs[i - 3], L, got[i - 3])
+                plan.run()
+        peer.push(seqs[11], loc_tot)
+        for i in range(9, 12):
+            peer.collect(seqs[i], L, got[i])
+        torch.cuda.synchronize()
+        want = sharding.all_reduce_totals(loc_tot.clone())
+        for t in got:
+            assert torch.allclose(t, want, rtol=1e-13), (t, want)
+        every = [torch.zeros_like(got[0]) for _ in range(world)]
+        dist.all_gather(every, got[0])
+        assert all(torch.equal(e, every[0]) for e in every), "peer totals differ between ranks"
+    peer.close()
+
     dist.barrier()
     if rank == 0:
-        print("multi-GPU check ok: world=%d, totals, outputs and entropy models agree with the unsharded run" % world)
+        print("multi-GPU check ok: world=%d, totals (NCCL and peer inboxes), outputs and entropy models agree with the unsharded run" % world)
     dist.destroy_process_group()
 
 

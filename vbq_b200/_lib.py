@@ -55,6 +55,14 @@ SIGNATURES = {
                           _p, _p, _p, _p, _p, _p, _p, _ll, _u, _p]),
     "vbq_quantize_hp": (_i, [_p, _p, _ll, _i, _p, _p, _i, _p, _p, _p, _i, _i, _p,
                              _p, _p, _p, _p, _p, _p, _p, _ll, _u, _p]),
+    "vbq_quantize_peer": (_i, [_p, _p, _ll, _i, _p, _p, _i, _p, _p, _p, _i, _i, _p,
+                               _p, _p, _p, _p, _p, _p, _p, _ll, _u, _p, _p, C.c_ulonglong, _p, C.c_ulonglong, _p]),
+    "vbq_peer_push": (_i, [_p, C.c_ulonglong, _i, _p, _p]),
+    "vbq_peer_ctx_create": (_i, [_i, _i, _i, C.POINTER(C.c_void_p)]),
+    "vbq_peer_ctx_handle": (_i, [_p, _p]),
+    "vbq_peer_ctx_connect": (_i, [_p, _p]),
+    "vbq_peer_ctx_destroy": (_i, [_p]),
+    "vbq_peer_collect": (_i, [_p, C.c_ulonglong, _i, _p, _p]),
     "vbq_host_ctx_create": (_i, [_i, _i, _i, _ll, _u, C.POINTER(C.c_void_p)]),
     "vbq_host_ctx_destroy": (_i, [_p]),
     "vbq_quantize_host": (_i, [_p, _p, _p, _ll, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p, _p, _p, _u]),

@@ -138,6 +138,19 @@ extern "C" int vbq_quantize_hp(const float *d_mu, const float *d_sigma, long lon
                                float *d_zhat, int *d_qidx, int *d_level, float *d_bits, float *d_em_bits,
                                double *d_totals, void *d_workspace, long long workspace_bytes, unsigned flags,
                                void *stream) {
+    return vbq_quantize_impl(d_mu, d_sigma, rows, C, d_table, d_packed, N, d_penalty, h_penalty, d_length, n_lambda,
+                             pen_channels, d_entropy_model, d_zhat, d_qidx, d_level, d_bits, d_em_bits, d_totals,
+                             d_workspace, workspace_bytes, flags, stream, nullptr);
+}
+
+// `push` (optional): where the last CTA of the search kernel also delivers this call's totals (peer.cu).  *push_fused
+// tells the caller whether a kernel did; otherwise the caller sends them with a kernel of its own.
+int vbq_quantize_impl(const float *d_mu, const float *d_sigma, long long rows, int C, const float *d_table,
+                      const float *d_packed, int N, const float *d_penalty, const float *h_penalty,
+                      const float *d_length, int n_lambda, int pen_channels, const float *d_entropy_model,
+                      float *d_zhat, int *d_qidx, int *d_level, float *d_bits, float *d_em_bits,
+                      double *d_totals, void *d_workspace, long long workspace_bytes, unsigned flags,
+                      void *stream, PeerPush *push) {
     if (rows < 0 || C < 1 || n_lambda < 1 || n_lambda > 65535 || (pen_channels != 1 && pen_channels != C))
         return vbq_fail(VBQ_ERR_BAD_SHAPE, "vbq_quantize: rows=%lld C=%d n_lambda=%d pen_channels=%d", rows, C,
                         n_lambda, pen_channels);
@@ -162,6 +175,9 @@ extern "C" int vbq_quantize_hp(const float *d_mu, const float *d_sigma, long lon
     a.em = d_entropy_model;
     a.zhat = d_zhat; a.qidx = d_qidx; a.level = d_level; a.bits = d_bits; a.em_bits = d_em_bits;
     a.totals = d_totals; a.partials = nullptr; a.ticket = nullptr; a.queue = nullptr;
+    a.peer_inbox = nullptr; a.peer_src = nullptr; a.peer_world = 0; a.peer_off = 0; a.peer_flag = 0; a.peer_seq = 0;
+    a.peer_own = nullptr; a.peer_coff = 0; a.peer_entry = 0; a.peer_cseq = 0; a.peer_cout = nullptr;
+    if (push) push->fused = false;
     a.flags = flags;
     a.one = 1;
     a.two = 2;
@@ -207,6 +223,14 @@ extern "C" int vbq_quantize_hp(const float *d_mu, const float *d_sigma, long lon
         if (d_bits) b.bits = d_bits + eo;
         if (d_em_bits) b.em_bits = d_em_bits + eo;
         b.accumulate = r0 > 0 || (flags & VBQ_FLAG_ACCUMULATE_TOTALS);
+        // one lambda, one chunk: the last CTA of the TMA kernels can deliver the totals to the peers itself
+        const bool can_fuse = push && n_lambda == 1 && rows <= max_chunk_rows && !b.accumulate;
+        if (can_fuse) {
+            b.peer_inbox = push->inbox; b.peer_world = push->world; b.peer_off = push->off; b.peer_flag = push->flag;
+            b.peer_seq = push->seq; b.peer_src = push->src;
+            b.peer_own = push->own; b.peer_coff = push->coff; b.peer_entry = push->entry; b.peer_cseq = push->cseq;
+            b.peer_cout = push->cout;
+        }
         int st_;
         if (!(flags & VBQ_FLAG_NO_SWEEP)) {   // several lambdas: one walk per coordinate serves all of them
             st_ = vbq_launch_sweep_bisect(b, dev, sms, st);
@@ -227,8 +251,12 @@ extern "C" int vbq_quantize_hp(const float *d_mu, const float *d_sigma, long lon
         else {
             // default: certified bisection (raw code lengths, N <= 10); otherwise the bracket walk in strict mode
             st_ = (flags & (VBQ_FLAG_BRACKET_WALK | VBQ_FLAG_NO_TMA)) ? -1 : vbq_launch_quantize_tma(b, dev, sms, st);
+            if (st_ >= 0 && can_fuse) push->fused = true;
             if (st_ < 0) st_ = (flags & VBQ_FLAG_BRACKET_WALK) ? -1 : vbq_launch_quantize_bisect(b, dev, sms, st);
-            if (st_ < 0) st_ = (flags & (VBQ_FLAG_BRACKET_WALK | VBQ_FLAG_NO_TMA)) ? -1 : vbq_launch_quantize_tma_both(b, dev, sms, st);
+            if (st_ < 0) {
+                st_ = (flags & (VBQ_FLAG_BRACKET_WALK | VBQ_FLAG_NO_TMA)) ? -1 : vbq_launch_quantize_tma_both(b, dev, sms, st);
+                if (st_ >= 0 && can_fuse) push->fused = true;
+            }
             if (st_ < 0) st_ = vbq_launch_quantize_strict(b, dev, sms, st);
         }
         RETURN_IF(st_);

@@ -381,6 +381,37 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
                 sts_v4(sm0 + kOffDesc + 16 * s_, -1, 0, 0, 0);
                 mbar_arrive(bar_full + 8 * s_);
             }
+        } else if (lane == 1 && blockIdx.x == gridDim.x - 1 && a.peer_world > 0) {
+            // Multi-GPU exchange of the totals (peer.cu), hidden behind this launch's search: an idle lane delivers the
+            // sums of an EARLIER call (complete: the wait above covers every earlier kernel of the stream) to every
+            // rank's inbox over NVLink (plain peer stores, then a system-scope release of the sequence number), and
+            // collects a still earlier call: waits for every rank's entry and adds them in rank order.
+            if (a.peer_seq) {
+                double v[VBQ_TOTALS];
+#pragma unroll
+                for (int k = 0; k < VBQ_TOTALS; ++k) v[k] = __ldcv(a.peer_src + k);
+                for (int p = 0; p < a.peer_world; ++p)
+#pragma unroll
+                    for (int k = 0; k < VBQ_TOTALS; ++k) a.peer_inbox[p][a.peer_off + k] = v[k];
+                __threadfence_system();
+                for (int p = 0; p < a.peer_world; ++p)
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.peer_inbox[p] + a.peer_flag), "l"(a.peer_seq) : "memory");
+            }
+            if (a.peer_cseq) {
+                for (int r = 0; r < a.peer_world; ++r) {
+                    const double *f = a.peer_own + a.peer_coff + (long long)r * a.peer_entry + (a.peer_entry - 1);
+                    unsigned long long v;
+                    do {
+                        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+                    } while (v < a.peer_cseq);
+                }
+#pragma unroll
+                for (int k = 0; k < VBQ_TOTALS; ++k) {
+                    double sum = 0.0;
+                    for (int r = 0; r < a.peer_world; ++r) sum += __ldcv(a.peer_own + a.peer_coff + (long long)r * a.peer_entry + k);
+                    a.peer_cout[k] = sum;
+                }
+            }
         }
         __syncwarp();
     } else {

@@ -174,8 +174,9 @@ class QuantizePlan:
     replays it (one cudaGraphLaunch per run)."""
 
     def __init__(self, mu, sigma, table, packed, penalty, length, entropy_model, max_bits, zhat=None, qidx=None,
-                 level=None, bits=None, em_bits=None, totals=None, flags=0, graph=False):
+                 level=None, bits=None, em_bits=None, totals=None, flags=0, graph=False, peer=None):
         self.totals = totals
+        self._peer = peer          # sharding.PeerTotals: run(seq) also delivers the totals to every rank's inbox
         self._device = mu.device
         ws = quantize_workspace(penalty.shape[0], mu.device) if totals is not None else None
         self._keep = (mu, sigma, table, packed, penalty, length, entropy_model, zhat, qidx, level, bits, em_bits, totals, ws)
@@ -207,6 +208,15 @@ class QuantizePlan:
             st = self._fn(*self._cargs, _stream(self._device))
         if st != _lib.OK:
             _lib.check(st, "vbq_quantize_hp")
+
+    def run_peer(self, push_seq=0, push_totals=None, collect_seq=0, collected=None):
+        """The call, which also delivers the completed totals of an earlier call (`push_totals`, sequence number
+        `push_seq`) to every rank and collects the all-reduced totals of call `collect_seq` into `collected`
+        (sharding.PeerTotals; include/vbq_b200.h vbq_quantize_peer)."""
+        st = self._peer._lib.vbq_quantize_peer(*self._cargs, _stream(self._device), self._peer._h, int(push_seq),
+                                               _ptr(push_totals), int(collect_seq), _ptr(collected))
+        if st != _lib.OK:
+            _lib.check(st, "vbq_quantize_peer")
 
     def run(self):
         if self._graph is not None:

@@ -50,6 +50,88 @@ def all_reduce_counts(counts, group=None):
     return counts
 
 
+class PeerTotals:
+    """All-reduce of the (n_lambda, 4) totals WITHOUT a collective launch (include/vbq_b200.h, csrc/peer.cu): the last CTA
+    of the search kernel writes the call's sums into every rank's inbox over NVLink; `collect(seq)` enqueues the wait for
+    all ranks' contributions to call `seq` and their sum in rank order.  One object per rank; the constructor exchanges
+    the 64-byte memory handles of the inboxes through torch.distributed (any backend).
+
+        peer = PeerTotals(n_lambda_max=64)
+        plan = ops.QuantizePlan(..., totals=local_totals, peer=peer)
+        plan.run(); seq = peer.next_seq()       # call number seq = 1, 2, 3, ... identical on all ranks
+        peer.push(seq, local_totals)            # or: the NEXT call does it while it runs, plan.run_peer(seq, local_totals, ...)
+        peer.collect(seq, n_lambda, global_totals)
+
+    Up to 8 calls may be delivered before the oldest is collected."""
+
+    def __init__(self, n_lambda_max=64, group=None, device=None):
+        import ctypes
+        from . import _lib
+        self._lib = _lib.load()
+        self.group = group
+        on = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if on else 0
+        self.world = dist.get_world_size(group) if on else 1
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.seq = 0
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.vbq_peer_ctx_create(self.rank, self.world, int(n_lambda_max), ctypes.byref(h)),
+                       "vbq_peer_ctx_create")
+            self._h = h
+            if self.world > 1:
+                mine = torch.zeros(64, dtype=torch.uint8)
+                _lib.check(self._lib.vbq_peer_ctx_handle(self._h, mine.data_ptr()), "vbq_peer_ctx_handle")
+                if dist.get_backend(group) == "nccl":
+                    every = [torch.zeros(64, dtype=torch.uint8, device=self.device) for _ in range(self.world)]
+                    dist.all_gather(every, mine.to(self.device), group=group)
+                    every = torch.stack(every).cpu()
+                else:
+                    every = [torch.zeros(64, dtype=torch.uint8) for _ in range(self.world)]
+                    dist.all_gather(every, mine, group=group)
+                    every = torch.stack(every)
+                every = every.contiguous()
+                _lib.check(self._lib.vbq_peer_ctx_connect(self._h, every.data_ptr()), "vbq_peer_ctx_connect")
+                dist.barrier(group)     # nobody writes into an inbox that is not mapped everywhere yet
+
+    def next_seq(self):
+        self.seq += 1
+        return self.seq
+
+    def push(self, seq, totals):
+        """Enqueue (on the current stream) the delivery of the (n_lambda, 4) totals of call `seq` to every rank."""
+        from . import _lib, ops
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.vbq_peer_push(self._h, int(seq), int(totals.shape[0]), totals.data_ptr(),
+                                               ops._stream(self.device)), "vbq_peer_push")
+
+    def collect(self, seq, n_lambda, out):
+        """Enqueue (on the current stream) the sum over ranks of call `seq` into `out` (n_lambda, 4) float64."""
+        from . import _lib, ops
+        if out.dtype != torch.float64 or tuple(out.shape) != (n_lambda, _lib.TOTALS) or not out.is_cuda:
+            raise ValueError("vbq_b200: `out` must be a (n_lambda, %d) float64 CUDA tensor" % _lib.TOTALS)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.vbq_peer_collect(self._h, int(seq), int(n_lambda), out.data_ptr(),
+                                                  ops._stream(self.device)), "vbq_peer_collect")
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None) is not None:
+            torch.cuda.synchronize(self.device)
+            if self.world > 1 and dist.is_initialized():
+                dist.barrier(self.group)    # nobody unmaps an inbox that a peer may still write to
+            self._lib.vbq_peer_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None:
+                self._lib.vbq_peer_ctx_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
 class ShardedQuantizer:
     """Data-parallel wrapper: each rank quantizes its slice and the per-lambda totals are all-reduced."""
 
