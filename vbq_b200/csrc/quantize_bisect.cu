@@ -218,14 +218,35 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_kernel(const QArgs a) 
             }
             int m_done = 0;   // deepest level scored (warp-uniform)
 
+            bool alive[U];            // DEEP: the coordinate still gathers from the global-memory depths
+            unsigned run_deep[U];     // DEEP: minimum of its keys so far
+#pragma unroll
+            for (int u = 0; u < U; ++u) { alive[u] = true; run_deep[u] = 0xffffffffu; }
+            auto deep_seed = [&](int u) -> unsigned {   // minimum over the shared-memory depths 0..kSmemDepth
+                unsigned m = key[u][0];
+#pragma unroll
+                for (int j = 1; j <= kSmemDepth; ++j) m = min(m, key[u][j]);
+                return m;
+            };
             // ---- depths 1..N, fully unrolled -------------------------------------------------------------
             auto depth = [&](auto n_tag) {
                 constexpr int n = decltype(n_tag)::value;
                 float z[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    if (n <= kSmemDepth) z[u] = lds_pure((unsigned)(imad((int)K[u], kRowStrideBytes, pbi) + 2 * n * kRowStrideBytes));
-                    else z[u] = __ldg(gT + K[u]);
+                    if (n <= kSmemDepth) {
+                        z[u] = lds_pure((unsigned)(imad((int)K[u], kRowStrideBytes, pbi) + 2 * n * kRowStrideBytes));
+                    } else {
+                        // Global-memory depths: a coordinate whose best key so far is more than the guard below the key of
+                        // pen_n cannot be won, or brought within the guard, by any deeper candidate (sound, like the
+                        // warp-wide early exit, but per coordinate): it stops gathering.  The gathers are the cost of
+                        // these depths (one 32-byte sector each), so this is what lambda >= 0.1 or so runs on.
+                        run_deep[u] = min(run_deep[u], n == kSmemDepth + 1 ? deep_seed(u) : key[u][n - 1]);
+                        const unsigned floor_key = __float_as_uint(pen[n]) & kmask;
+                        alive[u] = alive[u] && !(guard == kKeyGuard && floor_key > kKeyGuard + 32u &&
+                                                 run_deep[u] < floor_key - (kKeyGuard + 32u));
+                        z[u] = alive[u] ? __ldg(gT + K[u]) : CUDART_INF_F;
+                    }
                 }
 #pragma unroll
                 for (int k = 0; k < P; ++k) {
