@@ -98,3 +98,19 @@ def test_arbitrary_penalties_tma_equals_reference_walk(rows, C, lambs):
     ref, tr = _run(q, m, s, pen, len_t, em, ops.FLAG_REFERENCE_WALK, ("zhat", "bits", "em_bits"), N)
     new, tn = _run(q, m, s, pen, len_t, em, 0, ("zhat", "bits", "em_bits"), N)
     assert _same(ref, new) and _close(tn, tr)
+
+
+@pytest.mark.parametrize("rows,C", [(300, 1024), (50000, 16), (129, 4080), (5, 2000)])
+def test_work_distribution_variants(rows, C):
+    """More channel groups than tile queues (static row ranges, CTAs that span several groups), one group for all CTAs,
+    fewer tiles than CTAs; with and without totals (no workspace: static ranges)."""
+    N, lambs = 10, [0.5]
+    q, m, s = _case(rows, C, N, rows + C)
+    pen, length = q._length_tables(lambs)
+    ref, tr = _run(q, m, s, pen, length, None, ops.FLAG_NO_PRUNE | ops.FLAG_NO_TMA, ("qidx", "bits"), N)
+    new, tn = _run(q, m, s, pen, length, None, ops.FLAG_NO_PRUNE, ("qidx", "bits"), N)
+    assert _same(ref, new) and _close(tn, tr) and torch.equal(tn[:, :2], tr[:, :2])
+    o = {k: torch.full((1, rows, C), -7, dtype=DT[k], device=m.device) for k in ("qidx", "bits")}
+    ops.quantize_into(m, s, q.all_code_points, q._packed, pen, length, None, N, flags=ops.FLAG_NO_PRUNE, **o)
+    torch.cuda.synchronize()
+    assert _same(ref, o)

@@ -32,6 +32,30 @@ class ChannelwisePriorCDFQuantizer:
         self._cache = {}
         self._pipes = {}
 
+    # The fitted tables are plain dicts {lambda: ndarray} like in the reference (quantizer.py:110, :146).  Device copies of
+    # them are cached; ASSIGNING either attribute drops the cache.  After editing an entry of the dicts in place, call
+    # `invalidate_cache()` (the reference has no cache: it rebuilds the tensors on every call).
+    @property
+    def raw_code_length_entropy_models(self):
+        return self.__dict__.get('_rcl')
+
+    @raw_code_length_entropy_models.setter
+    def raw_code_length_entropy_models(self, value):
+        self.__dict__['_rcl'] = value
+        self.__dict__['_cache'] = {}
+
+    @property
+    def entropy_models(self):
+        return self.__dict__.get('_em')
+
+    @entropy_models.setter
+    def entropy_models(self, value):
+        self.__dict__['_em'] = value
+        self.__dict__['_cache'] = {}
+
+    def invalidate_cache(self):
+        self._cache = {}
+
     # ------------------------------------------------------------------------------------------------
     # code points (reference quantizer.py:25-63)
     # ------------------------------------------------------------------------------------------------
@@ -82,8 +106,7 @@ class ChannelwisePriorCDFQuantizer:
         """-> (penalty (L, 1|C, N+1), length or None) float32 device tensors."""
         N, C = self.max_bits_per_coord, self.num_channels
         corrected = bool(self.raw_code_length_entropy_models)
-        key = ("len", corrected, tuple(float(l) for l in lambs),
-               id(self.raw_code_length_entropy_models) if corrected else 0)
+        key = ("len", corrected, tuple(float(l) for l in lambs))
         if key in self._cache:
             return self._cache[key]
         lam32 = [np.float32(l) for l in lambs]
@@ -101,7 +124,7 @@ class ChannelwisePriorCDFQuantizer:
         return pen, length
 
     def _entropy_model_tensor(self, lambs):
-        key = ("em", tuple(float(l) for l in lambs), id(self.entropy_models))
+        key = ("em", tuple(float(l) for l in lambs))
         if key not in self._cache:
             em = np.stack([np.asarray(self.entropy_models[l], dtype=np.float32) for l in lambs])
             self._cache[key] = torch.from_numpy(np.ascontiguousarray(em)).to(self.device)
@@ -345,6 +368,8 @@ class ChannelwisePriorCDFQuantizer:
     # ------------------------------------------------------------------------------------------------
     def __getstate__(self):
         d = dict(self.__dict__)
+        d['raw_code_length_entropy_models'] = d.pop('_rcl', None)      # the reference's attribute names in the pickle
+        d['entropy_models'] = d.pop('_em', None)
         d['all_code_points'] = None if self.all_code_points is None else self.all_code_points.cpu().numpy()
         d['code_points_by_channel'] = None
         d['_packed'] = None
@@ -355,6 +380,9 @@ class ChannelwisePriorCDFQuantizer:
 
     def __setstate__(self, d):
         acp = d.pop('all_code_points')
+        d = dict(d)
+        d['_rcl'] = d.pop('raw_code_length_entropy_models', d.pop('_rcl', None))
+        d['_em'] = d.pop('entropy_models', d.pop('_em', None))
         self.__dict__.update(d)
         self.device = torch.device(self.device)
         self.all_code_points = None
