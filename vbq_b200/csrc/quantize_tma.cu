@@ -49,13 +49,10 @@ static int launch_tma3(const QArgs &a, int dev, int sms, cudaStream_t st) {
         const char *v = getenv("VBQ_TMA_VARIANT");
         const int vi = v ? atoi(v) : 0;
         if ((a.outm & 15u) == (2u | 8u) && vi > 0) {
-            if (vi == 1) return launch_tma<false, false, false, true, 10, 2 | 8, 17, 2>(a, a.qidx, a.bits, dev, sms, st);
-            if (vi == 2) return launch_tma<false, false, false, true, 10, 2 | 8, 21, 2>(a, a.qidx, a.bits, dev, sms, st);
-            if (vi == 3) return launch_tma<false, false, false, true, 10, 2 | 8, 19, 2>(a, a.qidx, a.bits, dev, sms, st);
-            if (vi == 4) return launch_tma<false, false, false, true, 10, 2 | 8, 23, 2>(a, a.qidx, a.bits, dev, sms, st);
-            if (vi == 5) return launch_tma<false, false, false, true, 10, 2 | 8, 11, 4>(a, a.qidx, a.bits, dev, sms, st);
-            if (vi == 6) return launch_tma<false, false, false, true, 10, 2 | 8, 13, 4>(a, a.qidx, a.bits, dev, sms, st);
-            if (vi == 7) return launch_tma<false, false, false, true, 10, 2 | 8, 9, 4>(a, a.qidx, a.bits, dev, sms, st);
+            if (vi == 1) return launch_tma<false, false, false, true, 10, 2 | 8, 20, 2>(a, a.qidx, a.bits, dev, sms, st);
+            if (vi == 2) return launch_tma<false, false, false, true, 10, 2 | 8, 22, 2>(a, a.qidx, a.bits, dev, sms, st);
+            if (vi == 3) return launch_tma<false, false, false, true, 10, 2 | 8, 18, 2>(a, a.qidx, a.bits, dev, sms, st);
+            if (vi == 4) return launch_tma<false, false, false, true, 10, 2 | 8, 21, 2>(a, a.qidx, a.bits, dev, sms, st);
         }
     }
 #endif
