@@ -303,21 +303,32 @@ class ChannelwisePriorCDFQuantizer:
         posterior_means, posterior_logvars = vae.encode(X)
         return self.build_entropy_models_from_latents(posterior_means, posterior_logvars, lambs, add_n_smoothing)
 
-    def _histograms(self, m, lv, lambs, what, reduce_fn=None, logvar=True):
-        """Per-(lambda, channel) counts of the chosen depth ('level', N+1 bins) or sorted index ('qidx', Q bins)."""
+    def _histograms(self, m, lv, lambs, what, reduce_fn=None, logvar=True, max_chunk_symbols=1 << 27):
+        """Per-(lambda, channel) counts of the chosen depth ('level', N+1 bins) or sorted index ('qidx', Q bins): the
+        np.bincount loops of quantizer.py:104-105 and :135-146.  The rows are searched in chunks of at most
+        ``max_chunk_symbols`` (lambda, coordinate) pairs — one walk per coordinate for all lambdas — and every chunk's
+        symbols are counted on the device by `vbq_symbol_histogram` (shared-memory histograms per 16-channel group), so
+        only the (Lambda, C, bins) int64 table outlives a chunk."""
         C, N, Q = self.num_channels, self.max_bits_per_coord, self.quantization_levels
+        L, rows = len(lambs), int(m.shape[0])
         nbins = N + 1 if what == 'level' else Q
-        out = self.quantize(m, lv, lambs, logvar=logvar, outputs=ops.OUT_LEVEL if what == 'level' else ops.OUT_QIDX)
-        sym = out[what]                                                      # (Lambda, rows, C) int32
+        # the histogram kernel counts symbols below 2^(b+1) - 1 for b <= 10: depths (<= 20) fit b = 4 (31 bins)
+        hist_bits = 4 if what == 'level' else N
+        kernel_ok = hist_bits <= 10
+        counts = torch.zeros((L, C, 2 ** (hist_bits + 1) - 1 if kernel_ok else nbins), dtype=torch.int64, device=self.device)
+        step = max(1, max_chunk_symbols // max(1, L * C))
         ch = torch.arange(C, device=self.device, dtype=torch.int64)
-        counts = []
-        for i in range(len(lambs)):
-            if what == 'qidx' and N <= 10:      # shared-memory histogram per 16-channel group (csrc/serialize.cu)
-                counts.append(ops.symbol_histogram(sym[i], N))
-                continue
-            flat = (sym[i].to(torch.int64) + ch[None, :] * nbins).reshape(-1)
-            counts.append(torch.bincount(flat, minlength=C * nbins).reshape(C, nbins))
-        counts = torch.stack(counts)
+        for a in range(0, rows, step):
+            out = self.quantize(m[a:a + step], lv[a:a + step], lambs, logvar=logvar,
+                                outputs=ops.OUT_LEVEL if what == 'level' else ops.OUT_QIDX)
+            sym = out[what]                                                  # (Lambda, chunk rows, C) int32
+            for i in range(L):
+                if kernel_ok:
+                    ops.symbol_histogram(sym[i], hist_bits, counts[i])
+                else:                                                        # N > 10: sorted indices beyond the kernel's bins
+                    flat = (sym[i].to(torch.int64) + ch[None, :] * nbins).reshape(-1)
+                    counts[i] += torch.bincount(flat, minlength=C * nbins).reshape(C, nbins)
+        counts = counts[:, :, :nbins].contiguous()
         if reduce_fn is not None:
             counts = reduce_fn(counts)
         return counts.cpu().numpy()
