@@ -435,22 +435,17 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
         for (int n = 0; n < kKeys; ++n) penc[n] = CUDART_INF_F;
 
         // one unit: U coordinates of this thread (unit rows par + 2u, channel col).  `mine` points at this thread's mu
-        // word of coordinate 0.  CHECK: some coordinates of the unit do not exist (`my_rows` rows do).
-        auto iteration = [&](auto check_tag, auto lv_tag, const unsigned mine, const int my_rows) {
-            constexpr bool CHECK = decltype(check_tag)::value;
-            constexpr bool LV = decltype(lv_tag)::value;
+        // word of coordinate 0; bit u of `okm`: coordinate u exists (the others were given harmless inputs by `prepare`).
+        auto iteration = [&](const unsigned mine, const unsigned okm) {
             float2 nmu2[P], r2[P];
             bool ok[U];
             {
                 float mu[U], sg[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    ok[u] = !CHECK || (c_ok && par + 2 * u < my_rows);
+                    ok[u] = (okm >> u) & 1u;
                     mu[u] = lds_u32(mine + u * 128);
-                    float s = lds_u32(mine + 4 * kSgOff + u * 128);
-                    if (CHECK && !ok[u]) { mu[u] = 0.0f; s = LV ? 0.0f : 1.0f; }
-                    if (LV) s = sqrtf(expf(s));
-                    sg[u] = s;
+                    sg[u] = lds_u32(mine + 4 * kSgOff + u * 128);
                 }
 #pragma unroll
                 for (int k = 0; k < P; ++k) {
@@ -565,9 +560,7 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
                 // the reloaded inputs — the whole warp for one coordinate when they are few, else every lane for itself
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    float m_ = lds_u32(mine + u * 128), s_ = lds_u32(mine + 4 * kSgOff + u * 128);
-                    if (CHECK && !ok[u]) { m_ = 0.0f; s_ = LV ? 0.0f : 1.0f; }
-                    if (LV) s_ = sqrtf(expf(s_));
+                    const float m_ = lds_u32(mine + u * 128), s_ = lds_u32(mine + 4 * kSgOff + u * 128);
                     unsigned todo = __ballot_sync(0xffffffffu, gap[u] <= kKeyGuard);
                     if (__popc(todo) <= 6) {
                         while (todo) {
@@ -631,21 +624,16 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
             for (int j = 1; j < kKeys; ++j) v = n == j ? penc[j] : v;
             return v;
         };
-        auto iteration_both = [&](auto check_tag, auto lv_tag, const unsigned mine, const int my_rows, const int unit_row) {
-            constexpr bool CHECK = decltype(check_tag)::value;
-            constexpr bool LV = decltype(lv_tag)::value;
+        auto iteration_both = [&](const unsigned mine, const unsigned okm, const int unit_row) {
             float2 nmu2[P], r2[P];
             bool ok[U];
             {
                 float mu[U], sg[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    ok[u] = !CHECK || (c_ok && par + 2 * u < my_rows);
+                    ok[u] = (okm >> u) & 1u;
                     mu[u] = lds_u32(mine + u * 128);
-                    float s = lds_u32(mine + 4 * kSgOff + u * 128);
-                    if (CHECK && !ok[u]) { mu[u] = 0.0f; s = LV ? 0.0f : 1.0f; }
-                    if (LV) s = sqrtf(expf(s));
-                    sg[u] = s;
+                    sg[u] = lds_u32(mine + 4 * kSgOff + u * 128);
                 }
 #pragma unroll
                 for (int k = 0; k < P; ++k) {
@@ -758,9 +746,7 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
             if (__any_sync(0xffffffffu, gap_min <= kKeyGuard)) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    float m_ = lds_u32(mine + u * 128), s_ = lds_u32(mine + 4 * kSgOff + u * 128);
-                    if (CHECK && !ok[u]) { m_ = 0.0f; s_ = LV ? 0.0f : 1.0f; }
-                    if (LV) s_ = sqrtf(expf(s_));
+                    const float m_ = lds_u32(mine + u * 128), s_ = lds_u32(mine + 4 * kSgOff + u * 128);
                     unsigned todo = __ballot_sync(0xffffffffu, gap[u] <= kKeyGuard);
                     if (__popc(todo) <= 6) {
                         while (todo) {
@@ -814,7 +800,24 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
             }
         };
 
-        auto run = [&](auto lv_tag) {
+        // Partial units (rows beyond the tile's share, channels beyond C) and log-variance inputs are handled BEFORE the
+        // search, in the slot: a thread rewrites its own words — sigma = sqrt(exp(logvar)) (quantizer.py:193-198), and
+        // mu = 0, sigma = 1 for coordinates that do not exist — so that ONE instance of the search serves every case.
+        auto prepare = [&](const unsigned mine, const int my_rows, const bool full) -> unsigned {
+            unsigned okm = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool ok = full || (c_ok && par + 2 * u < my_rows);
+                float m = lds_u32(mine + u * 128), sd = lds_u32(mine + 4 * kSgOff + u * 128);
+                if (logvar) sd = sqrtf(expf(sd));
+                if (!ok) { m = 0.0f; sd = 1.0f; }
+                sts_u32(mine + u * 128, __float_as_uint(m));
+                sts_u32(mine + 4 * kSgOff + u * 128, __float_as_uint(sd));
+                okm |= ok ? 1u << u : 0u;
+            }
+            return okm;
+        };
+        {
             int kk = __shfl_sync(0xffffffffu, claim_ticket(sm0 + kOffNext, lane), 0);
             for (;;) {
                 // the next ticket one iteration ahead; its value is read at the end of this iteration, so the atomic's
@@ -845,22 +848,18 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
                 }
                 const int my_rows = valid - (kk & (kUnits - 1)) * kUnitRows;   // rows of this unit that belong to the tile
                 const unsigned mine = lane_mu + (kk & (S * kUnits - 1)) * (kUnitFloats * 4);
-                if constexpr (BOTH) {
-                    const int unit_row = (kk & (kUnits - 1)) * kUnitRows;
-                    if (my_rows >= kUnitRows && group_full) iteration_both(std::false_type{}, lv_tag, mine, kUnitRows, unit_row);
-                    else if (my_rows > 0) iteration_both(std::true_type{}, lv_tag, mine, my_rows, unit_row);
-                } else {
-                    if (my_rows >= kUnitRows && group_full) iteration(std::false_type{}, lv_tag, mine, kUnitRows);
-                    else if (my_rows > 0) iteration(std::true_type{}, lv_tag, mine, my_rows);
+                if (my_rows > 0) {
+                    const bool full = my_rows >= kUnitRows && group_full;
+                    const unsigned okm = (full && !logvar) ? (1u << U) - 1u : prepare(mine, my_rows, full);
+                    if constexpr (BOTH) iteration_both(mine, okm, (kk & (kUnits - 1)) * kUnitRows);
+                    else iteration(mine, okm);
                 }
                 if (kNOut > 0) fence_proxy_async();   // this thread's st.shared -> visible to the TMA store
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_done + sb);
                 kk = __shfl_sync(0xffffffffu, nxt_raw, 0);
             }
-        };
-        if (logvar) run(std::true_type{});
-        else run(std::false_type{});
+        }
     }
 
 #ifdef VBQ_TRACE
