@@ -156,7 +156,7 @@ class ChannelwisePriorCDFQuantizer:
     # ------------------------------------------------------------------------------------------------
     # host arrays in, host arrays out: the chunked upload / kernel / download pipeline (vbq_quantize_host)
     # ------------------------------------------------------------------------------------------------
-    _HOST_CHUNK_ROWS = 9216
+    _HOST_CHUNK_ROWS = int(__import__('os').environ.get('VBQ_HOST_CHUNK_ROWS', 9216))
 
     @staticmethod
     def _is_host(x):
