@@ -529,14 +529,34 @@ def bench_corrected(q0, sets, world, dev, barrier, max_over_ranks):
     logvar = (2.0 * torch.log(b["sigma"])).contiguous()
     q.build_entropy_models_from_latents(b["mu"], logvar, grid, add_n_smoothing=1.0)
     out = {}
+    rows = b["mu"].shape[0]
     for name, lambs in (("single_lambda", [LAMB]), ("grid16", grid)):
+        # the C-ABI call with caller-owned buffers (ops.QuantizePlan, like the headline): what the kernels take
+        L = len(lambs)
+        pen, length = q._length_tables(lambs)
+        em = q._entropy_model_tensor(lambs)
+        z, bl, eb = (torch.empty((L, rows, C), dtype=torch.float32, device=dev) for _ in range(3))
+        res = {"lambdas": L, "unit": "coord-lambdas/s",
+               "outputs": "z_hat f32 + corrected code length f32 + entropy-model bits f32 + totals"}
+        for key, em_, eb_ in (("", em, eb), ("no_entropy_model_bits", None, None)):
+            plans = [ops.QuantizePlan(bb["mu"], bb["sigma"], q.all_code_points, q._packed, pen, length, em_, N_BITS, zhat=z,
+                                      bits=bl, em_bits=eb_, totals=torch.zeros((L, 4), dtype=torch.float64, device=dev))
+                     for bb in sets]
+            ms = max_over_ranks(_time_steps(lambda i: plans[i % len(plans)].run(), 20, 3, barrier)) / 20
+            r = {"ms_per_call": ms, "value": COORDS * L * world / (ms * 1e-3)}
+            if key:
+                res[key] = r
+            else:
+                res.update(r)
+            del plans
+        # the same through the facade (output allocation and table lookups per call: host-bound for one lambda)
+
         def fn(i, lambs=lambs):
             bb = sets[i % len(sets)]
             q.quantize(bb["mu"], bb["sigma"], lambs, outputs=ops.OUT_ZHAT | ops.OUT_BITS | ops.OUT_TOTALS, entropy_bits=True)
-        ms = max_over_ranks(_time_steps(fn, 10, 3, barrier))
-        out[name] = {"lambdas": len(lambs), "ms_per_call": ms / 10,
-                     "value": COORDS * len(lambs) * world * 10 / (ms * 1e-3), "unit": "coord-lambdas/s",
-                     "outputs": "z_hat f32 + corrected code length f32 + entropy-model bits f32 + totals"}
+        del z, bl, eb
+        res["facade_ms_per_call"] = max_over_ranks(_time_steps(fn, 10, 3, barrier)) / 10
+        out[name] = res
     return out
 
 

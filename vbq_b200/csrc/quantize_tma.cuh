@@ -180,7 +180,7 @@ static __device__ __forceinline__ int reference_search_warp(const float *sSc, co
 // NT > 0: max_bits_per_coord == NT at compile time; NT == 0: run time (<= kSmemDepth).
 // W = consumer warps (the CTA has W + 1 warps); P = coordinate pairs per thread: a warp iteration ("unit") covers
 // 4P consecutive rows x 16 channels, lane = (row parity, channel), coordinates at rows parity + 2u, u < 2P.
-template <bool BOTH, bool EM, bool PRUNE, bool TOTALS, int NT, int OUT, int W, int P>
+template <bool BOTH, int EM, bool PRUNE, bool TOTALS, int NT, int OUT, int W, int P>
 __global__ void __launch_bounds__(32 * (W + 1), 1)
     vbq_bisect_tma_kernel(const QArgs a, const __grid_constant__ TmaMaps maps, const UniformPen up) {
     constexpr int U = 2 * P, S = kSlots;
@@ -777,13 +777,15 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
                 if (TOTALS || (OUT & 1)) zh = lds_pure((unsigned)imad(Pn, kRowStrideBytes, (int)(t_sg + 4 * col)));
                 const float len = a.len ? __ldg(a.len + (size_t)(a.pen_channels == 1 ? 0 : chan) * (N + 1) + n) : (float)n;
                 float em = 0.0f;
-                if (EM) em = __ldg(a.em + (size_t)chan * a.Q + q);
+                if (EM == 1) em = __ldg(a.em + (size_t)chan * a.Q + q);
                 int slot_word = 0;
                 if (OUT & 1) { sts_u32(mine + slot_word * 4 * kSgOff + u * 128, __float_as_uint(zh * kWalkUnscale)); ++slot_word; }
                 if (OUT & 2) { sts_u32(mine + slot_word * 4 * kSgOff + u * 128, (unsigned)q); ++slot_word; }
                 if (OUT & 4) { sts_u32(mine + slot_word * 4 * kSgOff + u * 128, (unsigned)n); ++slot_word; }
-                if (OUT & 8) { sts_u32(mine + slot_word * 4 * kSgOff + u * 128, __float_as_uint(len)); ++slot_word; }
-                if (EM && a.em_bits && ok[u])
+                // EM == 2: the heap index of the winner travels in the code-length box; em_gather_kernel (quantize_tma_both.cu)
+                // turns it into the code length and entropy_model[c][q], the latter from a shared-memory copy of the group's table
+                if (OUT & 8) { sts_u32(mine + slot_word * 4 * kSgOff + u * 128, EM == 2 ? (unsigned)Pn : __float_as_uint(len)); ++slot_word; }
+                if (EM == 1 && a.em_bits && ok[u])
                     a.em_bits[((size_t)(tile_r0 + unit_row + par + 2 * u)) * C + chan] = em;
                 if (TOTALS && ok[u]) {
                     const float t = (zh + (u & 1 ? nmu2[u / 2].y : nmu2[u / 2].x)) * (u & 1 ? r2[u / 2].y : r2[u / 2].x);
@@ -796,7 +798,7 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
             if (TOTALS) {
                 acc_dist.add_q24(dsum);
                 acc_bits.add_q24(bsum);
-                if (EM) acc_em.add_q24(esum);
+                if (EM == 1) acc_em.add_q24(esum);
             }
         };
 
@@ -928,7 +930,7 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
 #endif
 }
 
-template <bool BOTH, bool EM, bool PRUNE, bool TOTALS, int NT, int OUT, int W, int P>
+template <bool BOTH, int EM, bool PRUNE, bool TOTALS, int NT, int OUT, int W, int P>
 static int launch_tma(const QArgs &a0, const void *out0, const void *out1, int dev, int sms, cudaStream_t st) {
     constexpr int kTile = kTmaRows;
     const long long rows4 = (a0.rows + 3) & ~3ll;
