@@ -52,7 +52,8 @@ def _same(a, b):
 
 
 def _close(t, r):
-    return float(((t - r).abs() / r.abs().clamp_min(1e-300)).max()) <= 2e-7
+    # terms are rounded to 2^-24 before the exact sum: relative for large totals, an absolute floor for tiny ones
+    return bool(((t - r).abs() <= 2e-7 * r.abs() + 1e-5).all())
 
 
 @pytest.mark.parametrize("rows,C,N,lambs", [(1, 16, 10, [0.5]), (17, 20, 10, [0.5]), (1000, 36, 10, [0.01, 2.0]),
@@ -73,27 +74,52 @@ def test_raw_lengths_tma_equals_reference_walk(rows, C, N, lambs):
             assert torch.equal(tn[:, 0], tr[:, 0])                       # depth sums are integers: exact
 
 
+def _lengths(style, rng, L, C, N):
+    """Corrected code lengths n + R[c, n] of several shapes: R pure noise (every depth can have a cheaper deeper
+    neighbour), like fitted tables (almost monotone, dips at a few shallow depths), monotone per channel, monotone with
+    a dip at one deep depth in a few channels, and all equal (ties between depths everywhere)."""
+    n = np.arange(N + 1, dtype=np.float32)[None, None, :]
+    if style == "noisy":
+        R = rng.gamma(2.0, 2.0, size=(L, C, N + 1))
+    elif style == "fitted":
+        R = 5.0 + 0.08 * (n - 3.0) ** 2 + rng.normal(0.0, 0.35, size=(L, C, N + 1))
+    elif style == "monotone":
+        return np.cumsum(rng.gamma(1.0, 1.0, size=(L, C, N + 1)), axis=2).astype(np.float32)
+    elif style == "deep_dip":
+        length = np.cumsum(rng.gamma(1.0, 1.0, size=(L, C, N + 1)) + 0.5, axis=2)
+        dip = rng.random((L, C)) < 0.2
+        length[..., 8] = np.where(dip, length[..., 6] - 0.25, length[..., 8])
+        return length.astype(np.float32)
+    else:
+        return np.full((L, C, N + 1), 3.0, dtype=np.float32)
+    return (n + R).astype(np.float32)
+
+
+@pytest.mark.parametrize("style", ["noisy", "fitted", "monotone", "deep_dip", "flat"])
 @pytest.mark.parametrize("rows,C,lambs", [(1, 16, [0.5]), (37, 20, [0.3]), (1000, 36, [0.01, 2.0]),
                                           (4099, 192, [0.5, 8.0, 0.0]), (20000, 64, [0.05])])
-def test_arbitrary_penalties_tma_equals_reference_walk(rows, C, lambs):
-    """Corrected code lengths n + R_lambda[c, n] with a non-monotone R, and the fused entropy-model gather."""
+def test_arbitrary_penalties_tma_equals_reference_walk(rows, C, lambs, style):
+    """Corrected code lengths n + R_lambda[c, n] and the entropy-model bits.  FLAG_NO_PRUNE makes the both-ends kernel
+    score the neighbour at every depth; by default it does so only where the penalties of a channel group allow the
+    neighbour to win."""
     N = 10
     q, m, s = _case(rows, C, N, 7 * rows + C)
     rng = np.random.default_rng(rows)
     L = len(lambs)
-    R = rng.gamma(2.0, 2.0, size=(L, C, N + 1)).astype(np.float32)
-    length = (np.arange(N + 1, dtype=np.float32)[None, None, :] + R).astype(np.float32)
+    length = _lengths(style, rng, L, C, N)
     pen = ops.with_host_copy(np.asarray(lambs, dtype=np.float32)[:, None, None] * length, m.device)
     len_t = torch.from_numpy(length).to(m.device)
     em = torch.from_numpy(rng.gamma(2.0, 3.0, size=(L, C, 2 ** (N + 1) - 1)).astype(np.float32)).to(m.device)
-    for outs, em_ in ((("zhat", "bits", "em_bits"), em), (("zhat", "bits"), em), (("zhat", "bits"), None),
-                      (("qidx",), None), ((), em), ((), None)):
+    combos = ((("zhat", "bits", "em_bits"), em), (("zhat", "bits"), em), (("zhat", "bits"), None),
+              (("qidx",), None), ((), em), ((), None))
+    for outs, em_ in combos if style in ("noisy", "fitted") else combos[:1] + combos[3:4]:
         f = ops.FLAG_NO_SWEEP
         ref, tr = _run(q, m, s, pen, len_t, em_, f | ops.FLAG_REFERENCE_WALK, outs, N)
-        new, tn = _run(q, m, s, pen, len_t, em_, f, outs, N)
-        new2, tn2 = _run(q, m, s, pen, len_t, em_, f, outs, N)
-        assert _same(ref, new), outs
-        assert torch.equal(tn, tn2) and _close(tn, tr)
+        for fl in (0, ops.FLAG_NO_PRUNE):
+            new, tn = _run(q, m, s, pen, len_t, em_, f | fl, outs, N)
+            new2, tn2 = _run(q, m, s, pen, len_t, em_, f | fl, outs, N)
+            assert _same(ref, new), (outs, fl)
+            assert torch.equal(tn, tn2) and _close(tn, tr)
     # several lambdas in one call (no NO_SWEEP) with the gather: per-lambda launches of the same kernel
     ref, tr = _run(q, m, s, pen, len_t, em, ops.FLAG_REFERENCE_WALK, ("zhat", "bits", "em_bits"), N)
     new, tn = _run(q, m, s, pen, len_t, em, 0, ("zhat", "bits", "em_bits"), N)

@@ -431,6 +431,9 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
         int range = -1, cur_tile = -1, valid = 0, tile_r0 = 0, chan = 0;
         bool c_ok = false, group_full = false;
         float penc[kKeys];   // BOTH: this thread's channel's penalties (per range)
+        // BOTH: depths at which the in-level neighbour of the path node can win for some channel of the group (see
+        // iteration_both); warp-uniform
+        unsigned bmask = 0;
 #pragma unroll
         for (int n = 0; n < kKeys; ++n) penc[n] = CUDART_INF_F;
 
@@ -618,6 +621,12 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
         // bracket's second point is the path node itself).  The one exception is mu above the highest point of depth
         // N, where the reference pairs the highest with the SECOND-highest point: those coordinates take the literal
         // search.
+        //   Most depths do not need the neighbour at all.  Between the path node of depth n and its neighbour lies exactly
+        // one coarser point, their lowest common ancestor A (depth a < n), which is on the search path; mu lies between the
+        // path node and A, so A is nearer to mu than the neighbour.  If pen[a] <= pen[n], A's float32 score is at least as
+        // good (monotone operations) and A comes first in the reference's candidate order: the neighbour cannot win.
+        // bmask holds the depths n with pen[n] < max(pen[0..n-1]) for some channel of the group — for fitted corrected
+        // lengths one to three shallow depths — and every other depth takes the raw-length step (one load).
         auto penc_at = [&](int n) -> float {   // penc[n] for a run-time n without moving the array to local memory
             float v = penc[0];
 #pragma unroll
@@ -666,6 +675,27 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
 #pragma unroll
                 for (int k = 0; k < P; ++k)
                     z[k] = make_float2(lds_pure(__float_as_uint(G[k].x)), lds_pure(__float_as_uint(G[k].y)));
+                if (!((bmask >> n) & 1u)) {   // the neighbour of this depth cannot win: the step of the raw-length search
+#pragma unroll
+                    for (int k = 0; k < P; ++k) {
+                        const float2 d = __fadd2_rn(z[k], nmu2[k]);
+                        const float2 st = make_float2(mul_sat(d.x, -1.7014118e38f), mul_sat(d.y, -1.7014118e38f));
+                        st_last[k] = st;
+                        if (n < kSmemDepth && (NT > 0 ? n < NT : true)) {
+                            float2 GL;
+                            if (n < kDblDepth) GL = __ffma2_rn(G[k], make_float2(2.0f, 2.0f), make_float2(Ec1, Ec1));
+                            else if (n == kDblDepth) GL = __fadd2_rn(G[k], make_float2(Esw, Esw));
+                            else GL = __ffma2_rn(G[k], make_float2(2.0f, 2.0f), make_float2(Ec2, Ec2));
+                            const float nstride = n < kDblDepth ? c128 : c64;
+                            G[k] = __ffma2_rn(st, make_float2(nstride, nstride), GL);
+                        }
+                        const float2 t = __fmul2_rn(d, r2[k]);
+                        const float2 A = __ffma2_rn(t, t, make_float2(penc[n], penc[n]));
+                        key[2 * k][n] = make_key<n>(A.x, kmask);
+                        key[2 * k + 1][n] = make_key<n>(A.y, kmask);
+                    }
+                    return;
+                }
 #pragma unroll
                 for (int k = 0; k < P; ++k) {
                     const float2 d = __fadd2_rn(z[k], nmu2[k]);
@@ -705,7 +735,8 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
             const int kd = m_done < kSmemDepth ? m_done + 1 : kSmemDepth;
 
             int wn[U], wP[U], Kd[U];
-            unsigned gap[U], gap_min = 0xffffffffu;
+            unsigned gap[U], mkey[U], gap_min = 0xffffffffu;
+            bool nb_any = false;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const unsigned *k_ = key[u];
@@ -723,26 +754,38 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
                 wn[u] = (int)(m & kDepthBits);
                 const unsigned gb = __float_as_uint(u & 1 ? G[u / 2].y : G[u / 2].x);
                 Kd[u] = kd <= kDblDepth ? (int)((gb - (t_db + 4 * lane)) >> 7) : (int)((gb - (t_sg + 4 * col)) >> 6);
-                // the two ends of the bracket at the winning depth: the path node and its neighbour on the side of the
-                // branch taken there (a path bit, or the last comparison at the deepest level)
-                const float sl = u & 1 ? st_last[u / 2].y : st_last[u / 2].x;
-                const int b = wn[u] < kd ? (Kd[u] >> (kd - wn[u] - 1)) & 1 : (sl != 0.0f ? 1 : 0);
-                const int Pp = Kd[u] >> (kd - wn[u]), Pq = Pp + 2 * b - 1;
-                const float nm_ = u & 1 ? nmu2[u / 2].y : nmu2[u / 2].x, r_ = u & 1 ? r2[u / 2].y : r2[u / 2].x;
-                const float dp = lds_pure((unsigned)imad(Pp, kRowStrideBytes, (int)(t_sg + 4 * col))) + nm_;
-                const float dq = wn[u] > 0 ? lds_pure((unsigned)imad(Pq, kRowStrideBytes, (int)(t_sg + 4 * col))) + nm_ : CUDART_INF_F;
-                // the nearer one wins; at equal distance the scores are equal and the left end comes first in the
-                // reference's candidate order.  Near-equal scores of the two ends: not certified.
-                const float ap = fabsf(dp), aq = fabsf(dq);
-                const bool take_q = aq < ap || (aq == ap && b == 0 && wn[u] > 0);
-                wP[u] = take_q ? Pq : Pp;
-                const float tf = fmaxf(ap, aq) * r_;
-                const int dfar = (int)(__float_as_uint(__fmaf_rn(tf, tf, penc_at(wn[u]))) & kmask) - (int)(m & kmask);
-                gap[u] = min(gap[u], dfar < 0 ? 0u : (unsigned)dfar);   // both keys are patterns of non-negative floats
+                wP[u] = Kd[u] >> (kd - wn[u]);
+                mkey[u] = m;
                 // mu above the highest point of the deepest level: the reference's bracket is (second highest, highest)
+                const float sl = u & 1 ? st_last[u / 2].y : st_last[u / 2].x;
                 if (Kd[u] == (2 << kd) - 1 && sl != 0.0f && kd == N) gap[u] = 0u;
-                gap_min = min(gap_min, gap[u]);
+                nb_any = nb_any || ((bmask >> wn[u]) & 1u);
             }
+            // the two ends of the bracket at the winning depth, where the neighbour can win (else the path node: its
+            // neighbour lost to an ancestor): the path node and its neighbour on the side of the branch taken there (a path
+            // bit, or the last comparison at the deepest level)
+            if (__any_sync(0xffffffffu, nb_any)) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool nb = (bmask >> wn[u]) & 1u;
+                    const float sl = u & 1 ? st_last[u / 2].y : st_last[u / 2].x;
+                    const int b = wn[u] < kd ? (Kd[u] >> (kd - wn[u] - 1)) & 1 : (sl != 0.0f ? 1 : 0);
+                    const int Pp = wP[u], Pq = Pp + 2 * b - 1;
+                    const float nm_ = u & 1 ? nmu2[u / 2].y : nmu2[u / 2].x, r_ = u & 1 ? r2[u / 2].y : r2[u / 2].x;
+                    const float dp = lds_pure((unsigned)imad(Pp, kRowStrideBytes, (int)(t_sg + 4 * col))) + nm_;
+                    const float dq = wn[u] > 0 ? lds_pure((unsigned)imad(Pq, kRowStrideBytes, (int)(t_sg + 4 * col))) + nm_ : CUDART_INF_F;
+                    // the nearer one wins; at equal distance the scores are equal and the left end comes first in the
+                    // reference's candidate order.  Near-equal scores of the two ends: not certified.
+                    const float ap = fabsf(dp), aq = fabsf(dq);
+                    const bool take_q = nb && (aq < ap || (aq == ap && b == 0 && wn[u] > 0));
+                    wP[u] = take_q ? Pq : Pp;
+                    const float tf = fmaxf(ap, aq) * r_;
+                    const int dfar = (int)(__float_as_uint(__fmaf_rn(tf, tf, penc_at(wn[u]))) & kmask) - (int)(mkey[u] & kmask);
+                    if (nb) gap[u] = min(gap[u], dfar < 0 ? 0u : (unsigned)dfar);   // both keys are patterns of non-negative floats
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) gap_min = min(gap_min, gap[u]);
             if (__any_sync(0xffffffffu, gap_min <= kKeyGuard)) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -845,6 +888,15 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
 #pragma unroll
                             for (int n = 0; n < kKeys; ++n)
                                 penc[n] = n <= N ? __ldg(a.pen + (size_t)(a.pen_channels == 1 ? 0 : chan) * (N + 1) + n) : CUDART_INF_F;
+                            unsigned below = 0;
+                            float pmax = penc[0];
+#pragma unroll
+                            for (int n = 1; n < kKeys; ++n)
+                                if (n <= N) {
+                                    below |= penc[n] < pmax ? 1u << n : 0u;
+                                    pmax = fmaxf(pmax, penc[n]);
+                                }
+                            bmask = (a.flags & VBQ_FLAG_NO_PRUNE) ? 0x7feu : __reduce_or_sync(0xffffffffu, below);
                         }
                     }
                 }
