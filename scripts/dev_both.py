@@ -107,6 +107,26 @@ def main():
             torch.cuda.synchronize()
             ms = ev[0].elapsed_time(ev[1]) / 20
             res["%s_L%d" % (name, L)] = {"ms_per_call": ms, "G_coord_lambda_s": bench.COORDS * L / ms / 1e6}
+    # totals only (the rate-distortion sweep after build_entropy_models): bracket-walk sweep vs one both-ends launch per lambda
+    for name, fl in (("totals_sweep", 0), ("totals_per_lambda", ops.FLAG_NO_SWEEP)):
+        for with_em in (True, False):
+            L = len(grid)
+            pen, length = q._length_tables(grid)
+            em = q._entropy_model_tensor(grid) if with_em else None
+            plans = [ops.QuantizePlan(mu, sg, q.all_code_points, q._packed, pen, length, em, bench.N_BITS,
+                                      totals=torch.zeros((L, 4), dtype=torch.float64, device=dev), flags=fl) for mu, sg in sets]
+            for i in range(3):
+                plans[i % 4].run()
+            torch.cuda.synchronize()
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            ev[0].record()
+            for i in range(10):
+                plans[i % 4].run()
+            ev[1].record()
+            torch.cuda.synchronize()
+            ms = ev[0].elapsed_time(ev[1]) / 10
+            res["%s_L16%s" % (name, "_em" if with_em else "")] = {"ms_per_call": ms, "G_coord_lambda_s": bench.COORDS * L / ms / 1e6,
+                                                                  "totals": plans[0].run()[3].tolist()}
     print(json.dumps(res, indent=1))
 
 

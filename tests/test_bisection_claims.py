@@ -69,6 +69,35 @@ def test_non_monotone_penalties_break_the_claim():
     assert (at_depth != Zo[0.5]).any()
 
 
+def test_neighbour_wins_only_below_the_running_maximum_of_the_penalties():
+    """DESIGN.md §2c (round 2): with arbitrary per-channel penalties the reference's winner is a path node, or the in-level
+    neighbour at a depth n whose penalty is below max(pen[0..n-1]) — elsewhere the neighbour loses to the ancestor it lies
+    beyond, which has a penalty no larger, is at least as near and comes first in the candidate order.  Penalties of
+    several shapes, ties included (repeated values, lambda = 0)."""
+    table, mu, sigma, oq = _setup(24, 10, 3000, 9)
+    nodes = path_nodes(table, mu)
+    rng = np.random.default_rng(3)
+    n_ = np.arange(11, dtype=F32)[None, :]
+    tables = {"noise": rng.uniform(0.25, 6.0, (24, 11)),
+              "fitted": 5.0 + 0.08 * (n_ - 3.0) ** 2 + rng.normal(0.0, 0.35, (24, 11)) ,
+              "steps": np.repeat(rng.uniform(0.0, 4.0, (24, 4)), 3, axis=1)[:, :11] - n_,      # plateaus: equal lengths
+              "dip": np.where((n_ == 8) & (rng.random((24, 1)) < 0.5), -3.0, 0.5 * n_)}
+    neighbours = 0
+    for name, R in tables.items():
+        for lam in (0.0, 2.0 ** -8, 0.5, 8.0):
+            oq.raw_code_length_entropy_models = {lam: R.astype(F32)}
+            Zo, Bo, det = oq.compress_batch_channel_latents(mu, sigma, [lam], details=True)
+            lvl = det[lam]["level"].astype(np.int64)
+            pen = (F32(lam) * oq.code_lengths([lam])[0].astype(F32)).astype(F32)          # (N+1, C), as the reference scores
+            below = np.zeros_like(pen, dtype=bool)
+            below[1:] = pen[1:] < np.maximum.accumulate(pen, axis=0)[:-1]
+            is_path = np.take_along_axis(nodes, lvl[None], axis=0)[0] == Zo[lam]
+            allowed = np.take_along_axis(below, lvl, axis=0)                            # (B, C): winner's depth is flagged
+            assert (is_path | allowed).all(), "%s, lambda=%g: a neighbour won at a depth where it should be dominated" % (name, lam)
+            neighbours += int((~is_path).sum())
+    assert neighbours > 0
+
+
 def _keys(z, mu, sigma, pen, rcp_ulps):
     """Bit patterns of the exact loss E and of the approximate loss A (float64 emulation of the single-rounding FMA)."""
     d = (z - mu).astype(F32)
