@@ -65,6 +65,9 @@ enum {
                                          on `stream` was enqueued (e.g. it synchronized after vbq_pack_code_points): the search
                                          kernel then fetches its code points while the stream's previous kernel still drains
                                          (programmatic dependent launch) instead of after it */
+#define VBQ_FLAG_NEIGHBOUR_EVERY_DEPTH 2048u /* arbitrary penalties (vbq_bisect_tma_kernel, both-ends variant): score the second
+                                          bracket end at every depth, not only where the penalties allow it to win (same
+                                          results; diagnostics and tests) */
 #define VBQ_FLAG_NO_TMA 512u           /* single lambda: stage the latents with per-warp cp.async (vbq_bisect_kernel) instead
                                          of the TMA pipeline (vbq_bisect_tma_kernel); same results, for comparison */
 #define VBQ_FLAG_BRACKET_WALK 128u     /* single lambda: use the nearer-bracket-end walk (strict mode) even where the

@@ -99,9 +99,9 @@ def _lengths(style, rng, L, C, N):
 @pytest.mark.parametrize("rows,C,lambs", [(1, 16, [0.5]), (37, 20, [0.3]), (1000, 36, [0.01, 2.0]),
                                           (4099, 192, [0.5, 8.0, 0.0]), (20000, 64, [0.05])])
 def test_arbitrary_penalties_tma_equals_reference_walk(rows, C, lambs, style):
-    """Corrected code lengths n + R_lambda[c, n] and the entropy-model bits.  FLAG_NO_PRUNE makes the both-ends kernel
-    score the neighbour at every depth; by default it does so only where the penalties of a channel group allow the
-    neighbour to win."""
+    """Corrected code lengths n + R_lambda[c, n] and the entropy-model bits.  FLAG_NEIGHBOUR_EVERY_DEPTH makes the
+    both-ends kernel score the neighbour at every depth; by default it does so only where the penalties of a channel
+    group allow the neighbour to win (FLAG_NO_PRUNE, which the facade sets for small lambdas, must not change that)."""
     N = 10
     q, m, s = _case(rows, C, N, 7 * rows + C)
     rng = np.random.default_rng(rows)
@@ -115,7 +115,7 @@ def test_arbitrary_penalties_tma_equals_reference_walk(rows, C, lambs, style):
     for outs, em_ in combos if style in ("noisy", "fitted") else combos[:1] + combos[3:4]:
         f = ops.FLAG_NO_SWEEP
         ref, tr = _run(q, m, s, pen, len_t, em_, f | ops.FLAG_REFERENCE_WALK, outs, N)
-        for fl in (0, ops.FLAG_NO_PRUNE):
+        for fl in (0, ops.FLAG_NEIGHBOUR_EVERY_DEPTH, ops.FLAG_NO_PRUNE):
             new, tn = _run(q, m, s, pen, len_t, em_, f | fl, outs, N)
             new2, tn2 = _run(q, m, s, pen, len_t, em_, f | fl, outs, N)
             assert _same(ref, new), (outs, fl)

@@ -21,6 +21,7 @@ FLAG_BRACKET_WALK = 128
 FLAG_WORKSPACE_ZEROED = 256
 FLAG_NO_TMA = 512
 FLAG_TABLE_STABLE = 1024
+FLAG_NEIGHBOUR_EVERY_DEPTH = 2048
 GROUP = 16
 TOTALS = 4
 PRIOR_PARAMS = 43

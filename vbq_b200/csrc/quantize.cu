@@ -157,7 +157,7 @@ int vbq_quantize_impl(const float *d_mu, const float *d_sigma, long long rows, i
     RETURN_IF(vbq_check_depth(N));
     if (flags & ~(VBQ_FLAG_LOGVAR | VBQ_FLAG_NO_PRUNE | VBQ_FLAG_FAST | VBQ_FLAG_ACCUMULATE_TOTALS | VBQ_FLAG_NO_SWEEP |
                   VBQ_FLAG_REFERENCE_WALK | VBQ_FLAG_RESERVE_SM | VBQ_FLAG_BRACKET_WALK | VBQ_FLAG_WORKSPACE_ZEROED |
-                  VBQ_FLAG_NO_TMA | VBQ_FLAG_TABLE_STABLE))
+                  VBQ_FLAG_NO_TMA | VBQ_FLAG_TABLE_STABLE | VBQ_FLAG_NEIGHBOUR_EVERY_DEPTH))
         return vbq_fail(VBQ_ERR_BAD_FLAGS, "vbq_quantize: unknown flag bits 0x%x", flags);
     if (!d_table || !d_packed || !d_penalty || (rows > 0 && (!d_mu || !d_sigma)))
         return vbq_fail(VBQ_ERR_NULL_POINTER, "vbq_quantize: null input pointer");

@@ -434,6 +434,7 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
         // BOTH: depths at which the in-level neighbour of the path node can win for some channel of the group (see
         // iteration_both); warp-uniform
         unsigned bmask = 0;
+        const float *lenp = nullptr;   // BOTH: this thread's channel's row of the code-length table
 #pragma unroll
         for (int n = 0; n < kKeys; ++n) penc[n] = CUDART_INF_F;
 
@@ -668,14 +669,15 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
                 key[2 * k][0] = make_key<0>(A.x, kmask);
                 key[2 * k + 1][0] = make_key<0>(A.y, kmask);
             }
-            auto depth = [&](auto n_tag) {
+            auto depth = [&](auto n_tag, auto raw_tag) {
                 constexpr int n = decltype(n_tag)::value;
+                constexpr bool kRawOnly = decltype(raw_tag)::value;       // the caller knows that bit n of bmask is clear
                 const float stride = n <= kDblDepth ? c128 : c64;         // row pitch of the level the node sits in
                 float2 z[P];
 #pragma unroll
                 for (int k = 0; k < P; ++k)
                     z[k] = make_float2(lds_pure(__float_as_uint(G[k].x)), lds_pure(__float_as_uint(G[k].y)));
-                if (!((bmask >> n) & 1u)) {   // the neighbour of this depth cannot win: the step of the raw-length search
+                if (kRawOnly || !((bmask >> n) & 1u)) {   // the neighbour of this depth cannot win: the step of the raw-length search
 #pragma unroll
                     for (int k = 0; k < P; ++k) {
                         const float2 d = __fadd2_rn(z[k], nmu2[k]);
@@ -722,21 +724,29 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
                 }
             };
             int m_done = 0;
-#define VBQ_DEPTH(n_)                                                                                          \
+#define VBQ_DEPTH(n_, raw_)                                                                                    \
     if constexpr (n_ <= kSmemDepth) {                                                                          \
         if (NT > 0 ? n_ <= NT : n_ <= N) {                                                                     \
-            depth(std::integral_constant<int, n_>{});                                                          \
+            depth(std::integral_constant<int, n_>{}, std::integral_constant<bool, raw_>{});                    \
             m_done = n_;                                                                                       \
         }                                                                                                      \
     }
-            VBQ_DEPTH(1) VBQ_DEPTH(2) VBQ_DEPTH(3) VBQ_DEPTH(4) VBQ_DEPTH(5)
-            VBQ_DEPTH(6) VBQ_DEPTH(7) VBQ_DEPTH(8) VBQ_DEPTH(9) VBQ_DEPTH(10)
+            // fitted corrected lengths dip at the shallow depths only: from depth 4 on, one test selects a branch-free run of
+            // raw-length steps (which the compiler schedules across depths) or the per-depth tests
+            VBQ_DEPTH(1, false) VBQ_DEPTH(2, false) VBQ_DEPTH(3, false)
+            if ((bmask >> 4) == 0u) {
+                VBQ_DEPTH(4, true) VBQ_DEPTH(5, true) VBQ_DEPTH(6, true) VBQ_DEPTH(7, true)
+                VBQ_DEPTH(8, true) VBQ_DEPTH(9, true) VBQ_DEPTH(10, true)
+            } else {
+                VBQ_DEPTH(4, false) VBQ_DEPTH(5, false) VBQ_DEPTH(6, false) VBQ_DEPTH(7, false)
+                VBQ_DEPTH(8, false) VBQ_DEPTH(9, false) VBQ_DEPTH(10, false)
+            }
 #undef VBQ_DEPTH
             const int kd = m_done < kSmemDepth ? m_done + 1 : kSmemDepth;
 
             int wn[U], wP[U], Kd[U];
             unsigned gap[U], mkey[U], gap_min = 0xffffffffu;
-            bool nb_any = false;
+            int wn_min = kKeys;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const unsigned *k_ = key[u];
@@ -756,11 +766,17 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
                 Kd[u] = kd <= kDblDepth ? (int)((gb - (t_db + 4 * lane)) >> 7) : (int)((gb - (t_sg + 4 * col)) >> 6);
                 wP[u] = Kd[u] >> (kd - wn[u]);
                 mkey[u] = m;
-                // mu above the highest point of the deepest level: the reference's bracket is (second highest, highest)
-                const float sl = u & 1 ? st_last[u / 2].y : st_last[u / 2].x;
-                if (Kd[u] == (2 << kd) - 1 && sl != 0.0f && kd == N) gap[u] = 0u;
-                nb_any = nb_any || ((bmask >> wn[u]) & 1u);
+                wn_min = min(wn_min, wn[u]);
             }
+            // mu above the highest point of the deepest level: the reference's bracket is (second highest, highest)
+            if (kd == N && ((bmask >> N) & 1u)) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float sl = u & 1 ? st_last[u / 2].y : st_last[u / 2].x;
+                    if (Kd[u] == (2 << kd) - 1 && sl != 0.0f) gap[u] = 0u;
+                }
+            }
+            const bool nb_any = wn_min < 32 - __clz(bmask);   // some winner is no deeper than the deepest masked depth
             // the two ends of the bracket at the winning depth, where the neighbour can win (else the path node: its
             // neighbour lost to an ancestor): the path node and its neighbour on the side of the branch taken there (a path
             // bit, or the last comparison at the deepest level)
@@ -818,7 +834,7 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
                 const int q = ((2 * Pn + 1) << (N - n)) - (2 << N) - 1;
                 float zh = 0.0f;   // scaled by 2^24
                 if (TOTALS || (OUT & 1)) zh = lds_pure((unsigned)imad(Pn, kRowStrideBytes, (int)(t_sg + 4 * col)));
-                const float len = a.len ? __ldg(a.len + (size_t)(a.pen_channels == 1 ? 0 : chan) * (N + 1) + n) : (float)n;
+                const float len = lenp ? __ldg(lenp + n) : (float)n;
                 float em = 0.0f;
                 if (EM == 1) em = __ldg(a.em + (size_t)chan * a.Q + q);
                 int slot_word = 0;
@@ -888,6 +904,7 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
 #pragma unroll
                             for (int n = 0; n < kKeys; ++n)
                                 penc[n] = n <= N ? __ldg(a.pen + (size_t)(a.pen_channels == 1 ? 0 : chan) * (N + 1) + n) : CUDART_INF_F;
+                            lenp = a.len ? a.len + (size_t)(a.pen_channels == 1 ? 0 : chan) * (N + 1) : nullptr;
                             unsigned below = 0;
                             float pmax = penc[0];
 #pragma unroll
@@ -896,7 +913,7 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
                                     below |= penc[n] < pmax ? 1u << n : 0u;
                                     pmax = fmaxf(pmax, penc[n]);
                                 }
-                            bmask = (a.flags & VBQ_FLAG_NO_PRUNE) ? 0x7feu : __reduce_or_sync(0xffffffffu, below);
+                            bmask = (a.flags & VBQ_FLAG_NEIGHBOUR_EVERY_DEPTH) ? 0x7feu : __reduce_or_sync(0xffffffffu, below);
                         }
                     }
                 }

@@ -28,6 +28,7 @@ FLAG_BRACKET_WALK = _lib.FLAG_BRACKET_WALK
 FLAG_WORKSPACE_ZEROED = _lib.FLAG_WORKSPACE_ZEROED
 FLAG_NO_TMA = _lib.FLAG_NO_TMA
 FLAG_TABLE_STABLE = _lib.FLAG_TABLE_STABLE
+FLAG_NEIGHBOUR_EVERY_DEPTH = _lib.FLAG_NEIGHBOUR_EVERY_DEPTH
 
 
 def _ptr(t: Optional[torch.Tensor]):
