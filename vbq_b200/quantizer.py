@@ -13,6 +13,25 @@ import torch
 from . import ops, utils
 
 
+_PINNED = {}   # (shape, dtype) -> pinned staging buffer for count tables (allocated once: cudaHostAlloc takes ~100 ms)
+
+
+def _counts_to_host(counts):
+    """int64 device counts -> NumPy.  The (Lambda, C, Q) table of a 16-lambda fit is 50 MB as int64: a pageable
+    `.cpu()` of it took 22 ms of a 45 ms fit; as int32 through a reused pinned buffer it takes 0.5 ms.  Counts beyond
+    int32 (more than 2^31 - 1 rows) keep the int64 path."""
+    if counts.numel() == 0 or not counts.is_cuda or int(counts.max()) >= 2 ** 31:
+        return counts.cpu().numpy()
+    c32 = counts.to(torch.int32)
+    key = (tuple(c32.shape), c32.dtype)
+    if key not in _PINNED:
+        _PINNED[key] = torch.empty(c32.shape, dtype=c32.dtype, pin_memory=True)
+    host = _PINNED[key]
+    host.copy_(c32, non_blocking=True)
+    torch.cuda.current_stream(counts.device).synchronize()
+    return host.numpy().copy()
+
+
 class ChannelwisePriorCDFQuantizer:
     def __init__(self, num_channels, max_bits_per_coord, float_type='float32', int_type='int32', device='cuda'):
         # reference quantizer.py:14-23
@@ -331,7 +350,7 @@ class ChannelwisePriorCDFQuantizer:
         counts = counts[:, :, :nbins].contiguous()
         if reduce_fn is not None:
             counts = reduce_fn(counts)
-        return counts.cpu().numpy()
+        return _counts_to_host(counts)
 
     def build_entropy_models_from_latents(self, posterior_means, posterior_logvars, lambs, add_n_smoothing,
                                           reduce_fn=None, posterior_stds=None):
