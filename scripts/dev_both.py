@@ -80,7 +80,7 @@ def main():
     grid = [float(l) for l in 2.0 ** np.linspace(-8, 7, 16)]
     q.build_entropy_models_from_latents(sets[0][0], (2.0 * torch.log(sets[0][1])).contiguous(), grid, add_n_smoothing=1.0)
     res = {}
-    runs = [("both", 0, "0"), ("both_every_depth", ops.FLAG_NEIGHBOUR_EVERY_DEPTH, "0"), ("bracket_walk", ops.FLAG_BRACKET_WALK, "0")] + [("both_v" + v, 0, v) for v in args.variants.split(",") if v]
+    runs = [("both", 0, "0"), ("sweep", 0, "0"), ("both_every_depth", ops.FLAG_NEIGHBOUR_EVERY_DEPTH, "0"), ("bracket_walk", ops.FLAG_BRACKET_WALK, "0")] + [("both_v" + v, 0, v) for v in args.variants.split(",") if v]
     rows, C = sets[0][0].shape
     for name, fl, var in runs:
         os.environ["VBQ_TMA_VARIANT"] = var

@@ -211,7 +211,11 @@ def test_sweep_equals_per_lambda_walks(N, C, rows, n_lambda, corrected, fast):
     for k in ("zhat", "qidx", "level", "bits", "em_bits"):
         assert torch.equal(a[k], b[k]), k
     assert torch.allclose(a["totals"], b["totals"], rtol=1e-6, atol=1e-9)
-    assert torch.equal(a["totals"][:, :3], b["totals"][:, :3])     # integer / float sums of identical terms
+    # depth sums are integers; raw code lengths too.  Corrected lengths / entropy-model bits are float32 terms that the
+    # sweep kernel adds per 64-coordinate tile (units of 2^-16) and the per-lambda kernels per 4 coordinates (2^-24)
+    assert torch.equal(a["totals"][:, :1], b["totals"][:, :1])
+    if not corrected:
+        assert torch.equal(a["totals"][:, :3], b["totals"][:, :3])
 
 
 def test_strict_mode_equals_reference_walk():

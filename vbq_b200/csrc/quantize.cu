@@ -179,6 +179,7 @@ int vbq_quantize_impl(const float *d_mu, const float *d_sigma, long long rows, i
     a.peer_own = nullptr; a.peer_coff = 0; a.peer_entry = 0; a.peer_cseq = 0; a.peer_cout = nullptr;
     if (push) push->fused = false;
     a.flags = flags;
+    a.kout = 0;
     a.one = 1;
     a.two = 2;
     a.keymask = 0xfffffff0u;
@@ -237,6 +238,8 @@ int vbq_quantize_impl(const float *d_mu, const float *d_sigma, long long rows, i
             // corrected code lengths with per-coordinate outputs: one launch of the both-ends TMA kernel per lambda is faster
             // than the bracket-walk sweep (measured, 16 lambdas on the Kodak batch: 1.40 vs 1.97 ms with the entropy-model
             // bits, 0.91 vs 1.16 ms without); totals-only sweeps stay with the sweep kernel (0.77 vs 0.87 ms)
+            // arbitrary penalties, several lambdas: the both-ends sweep (one walk for all lambdas)
+            if (st_ < 0 && !getenv("VBQ_NO_SWEEP_BOTH")) st_ = vbq_launch_sweep_both(b, dev, sms, st);
             if (st_ < 0 && n_lambda > 1 && (b.outm & 15u) &&
                 !(flags & (VBQ_FLAG_BRACKET_WALK | VBQ_FLAG_NO_TMA | VBQ_FLAG_FAST | VBQ_FLAG_REFERENCE_WALK)))
                 st_ = vbq_launch_quantize_tma_both(b, dev, sms, st);

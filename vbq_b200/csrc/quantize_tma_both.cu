@@ -163,6 +163,13 @@ static int launch_em_gather(const QArgs &a, int dev, int sms, cudaStream_t st) {
     return launch(em_gather_kernel<false>, (double *)nullptr, (Acc128 *)nullptr, (unsigned *)nullptr);
 }
 
+// For vbq_both_sweep_kernel (sweep_both.cu), which leaves the winners' heap indices in the code-length planes of all lambdas
+int vbq_launch_em_gather(const QArgs &a, int dev, int sms, cudaStream_t st) {
+    if (a.N != kSmemDepth || !a.em || !a.em_bits || !a.bits || a.C % 4 != 0 || a.n_groups > 2 * kMaxGrid || a.n_lambda > 65535) return -1;
+    if ((((uintptr_t)a.em_bits | (uintptr_t)a.em | (uintptr_t)a.bits) & 15) != 0) return -1;
+    return launch_em_gather(a, dev, sms, st);
+}
+
 template <int EM, bool TOTALS, int OUT>
 static int launch_both(const QArgs &a, const void *out0, const void *out1, int dev, int sms, cudaStream_t st) {
 #ifdef VBQ_DEV_VARIANTS
