@@ -131,6 +131,25 @@ def test_arbitrary_penalties_tma_equals_reference_walk(rows, C, lambs, style):
             assert torch.equal(tn, tn2) and _close(tn, tr, 2e-6), (outs, fl, tn, tr)
 
 
+@pytest.mark.parametrize("rows,C,N,L", [(700, 20, 6, 5), (3000, 48, 10, 40), (64, 16, 1, 2), (5000, 36, 9, 3)])
+def test_both_ends_sweep_small_depths_and_lambda_chunks(rows, C, N, L):
+    """csrc/sweep_both.cu with max_bits_per_coord < 10 (entropy-model bits gathered in the kernel: em_gather_kernel serves
+    N = 10 only), with more lambdas than one launch holds (28), and with entropy-model bits but no code-length output."""
+    q, m, s = _case(rows, C, N, rows + N)
+    rng = np.random.default_rng(rows + L)
+    lambs = [float(l) for l in 2.0 ** np.linspace(-8, 6, L)]
+    length = _lengths("fitted" if N > 3 else "noisy", rng, L, C, N)
+    pen = ops.with_host_copy(np.asarray(lambs, dtype=np.float32)[:, None, None] * length, m.device)
+    len_t = torch.from_numpy(length).to(m.device)
+    em = torch.from_numpy(rng.gamma(2.0, 3.0, size=(L, C, 2 ** (N + 1) - 1)).astype(np.float32)).to(m.device)
+    for outs, em_ in ((("zhat", "bits", "em_bits"), em), (("zhat", "em_bits"), em), (("qidx", "level"), None), ((), em)):
+        ref, tr = _run(q, m, s, pen, len_t, em_, ops.FLAG_REFERENCE_WALK, outs, N)
+        new, tn = _run(q, m, s, pen, len_t, em_, 0, outs, N)
+        new2, tn2 = _run(q, m, s, pen, len_t, em_, 0, outs, N)
+        assert _same(ref, new), outs
+        assert torch.equal(tn, tn2) and _close(tn, tr, 2e-6), (outs, tn, tr)
+
+
 @pytest.mark.parametrize("rows,C", [(300, 1024), (50000, 16), (129, 4080), (5, 2000)])
 def test_work_distribution_variants(rows, C):
     """More channel groups than tile queues (static row ranges, CTAs that span several groups), one group for all CTAs,

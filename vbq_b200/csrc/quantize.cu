@@ -235,9 +235,10 @@ int vbq_quantize_impl(const float *d_mu, const float *d_sigma, long long rows, i
         int st_;
         if (!(flags & VBQ_FLAG_NO_SWEEP)) {   // several lambdas: one walk per coordinate serves all of them
             st_ = vbq_launch_sweep_bisect(b, dev, sms, st);
-            // corrected code lengths with per-coordinate outputs: one launch of the both-ends TMA kernel per lambda is faster
-            // than the bracket-walk sweep (measured, 16 lambdas on the Kodak batch: 1.40 vs 1.97 ms with the entropy-model
-            // bits, 0.91 vs 1.16 ms without); totals-only sweeps stay with the sweep kernel (0.77 vs 0.87 ms)
+            // where the both-ends sweep does not apply (C % 4, unaligned arrays, no host copy of the penalties): with
+            // per-coordinate outputs one launch of the both-ends TMA kernel per lambda is faster than the bracket-walk sweep
+            // (measured, 16 lambdas on the Kodak batch: 1.40 vs 1.97 ms with the entropy-model bits, 0.91 vs 1.16 ms
+            // without); totals-only sweeps go to the bracket-walk sweep (0.77 vs 0.87 ms)
             // arbitrary penalties, several lambdas: the both-ends sweep (one walk for all lambdas)
             if (st_ < 0 && !getenv("VBQ_NO_SWEEP_BOTH")) st_ = vbq_launch_sweep_both(b, dev, sms, st);
             if (st_ < 0 && n_lambda > 1 && (b.outm & 15u) &&
