@@ -134,11 +134,14 @@ def test_arbitrary_penalties_tma_equals_reference_walk(rows, C, lambs, style):
 @pytest.mark.parametrize("rows,C,N,L", [(700, 20, 6, 5), (3000, 48, 10, 40), (64, 16, 1, 2), (5000, 36, 9, 3)])
 def test_both_ends_sweep_small_depths_and_lambda_chunks(rows, C, N, L):
     """csrc/sweep_both.cu with max_bits_per_coord < 10 (entropy-model bits gathered in the kernel: em_gather_kernel serves
-    N = 10 only), with more lambdas than one launch holds (28), and with entropy-model bits but no code-length output."""
+    N = 10 only), with more lambdas than one launch holds (18), with entropy-model bits but no code-length output, and with
+    code lengths beyond 512 bits."""
     q, m, s = _case(rows, C, N, rows + N)
     rng = np.random.default_rng(rows + L)
     lambs = [float(l) for l in 2.0 ** np.linspace(-8, 6, L)]
     length = _lengths("fitted" if N > 3 else "noisy", rng, L, C, N)
+    if N == 9:
+        length = (length * np.float32(200.0)).astype(np.float32)   # beyond 512 bits: the totals take the float32 butterfly
     pen = ops.with_host_copy(np.asarray(lambs, dtype=np.float32)[:, None, None] * length, m.device)
     len_t = torch.from_numpy(length).to(m.device)
     em = torch.from_numpy(rng.gamma(2.0, 3.0, size=(L, C, 2 ** (N + 1) - 1)).astype(np.float32)).to(m.device)

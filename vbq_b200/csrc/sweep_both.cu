@@ -18,7 +18,7 @@
 
 #include "bisect.cuh"
 
-constexpr int kPenSlots = 12;   // per (lambda, channel): penalties of depths 0..10, 48 bytes (three float4)
+constexpr int kPenSlots = 24;   // per (lambda, channel): penalties of depths 0..10 (three float4), then the code lengths of depths 0..10
 constexpr int kAccPerLambda = 4;   // sum n, sum code length, sum entropy-model bits, sum distortion
 
 // OUTS: per-coordinate outputs are requested (otherwise the call returns only the per-lambda totals); EM: entropy-model bits
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_both_sweep_kernel(const QArgs
     float *sStage = sPenL + (size_t)L * VBQ_GROUP * kPenSlots;   // [kWarps][kStages][kTileFloats] staging rings
     long long *sAcc = reinterpret_cast<long long *>(sStage + kWarps * kStages * kTileFloats);   // [kWarps][L][4], integers
     unsigned *sMask = reinterpret_cast<unsigned *>(sAcc + (TOTALS ? (size_t)kWarps * L * kAccPerLambda : 0));   // [L]
-    __shared__ int sNext;
+    __shared__ int sNext, sBig;   // sBig: some code length exceeds 512 bits (the integer warp sums below would overflow)
     __shared__ bool sLast;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -59,6 +59,8 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_both_sweep_kernel(const QArgs
     if (TOTALS) {
         for (int k = threadIdx.x; k < kWarps * L * kAccPerLambda; k += kThreads) sAcc[k] = 0;
     }
+    if (threadIdx.x == 0) sBig = 0;
+    __syncthreads();
     pdl_wait();   // launched with programmatic stream serialization: nothing global is touched before this point
     long long unit = u0;
     while (unit < u1) {
@@ -71,15 +73,20 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_both_sweep_kernel(const QArgs
         if (threadIdx.x == 0) sNext = 0;
         // the penalties of the group's channels for every lambda (quantizer.py:170-180: lambda * (n + R_lambda[c, n]))
         for (int k = threadIdx.x; k < L * VBQ_GROUP * kPenSlots; k += kThreads) {
-            const int n = k % kPenSlots, j = (k / kPenSlots) % VBQ_GROUP, lam = k / (kPenSlots * VBQ_GROUP);
+            const int n = k % 12, what = (k / 12) & 1, j = (k / kPenSlots) % VBQ_GROUP, lam = k / (kPenSlots * VBQ_GROUP);
             const int ch = a.pen_channels == 1 ? 0 : min(g * VBQ_GROUP + j, C - 1);
-            sPenL[k] = n <= N ? __ldg(a.pen + ((size_t)lam * a.pen_channels + ch) * (N + 1) + n) : CUDART_INF_F;
+            const size_t src = ((size_t)lam * a.pen_channels + ch) * (N + 1) + n;
+            float v = what ? (float)n : CUDART_INF_F;          // no length table: raw code lengths
+            if (n <= N) v = what ? (a.len ? __ldg(a.len + src) : (float)n) : __ldg(a.pen + src);
+            sPenL[k] = v;
+            if (what && !(v <= 512.0f)) sBig = 1;
         }
         __syncthreads();
         // depths at which the in-level neighbour can win for some lambda and some channel of the group: pen_n below the
         // running maximum of the shallower depths (warp-uniform; every warp computes the same mask)
         // sMask[lam]: the same per lambda (the walk serves all lambdas and uses the union; the decision between the two ends
         // of a winning depth uses the lambda's own mask)
+        const bool big = sBig != 0;
         unsigned umask = 0;
         for (int lam = 0; lam < L; ++lam) {
             const float *pr = sPenL + (lam * VBQ_GROUP + col) * kPenSlots;
@@ -204,7 +211,8 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_both_sweep_kernel(const QArgs
             // lane j of the warp keeps the tile's sums of lambda lb + j; they reach shared memory once per 32 lambdas
             for (int lb = 0; lb < L; lb += 32) {
             int my_level = 0;
-            float my_bits = 0.0f, my_em = 0.0f, my_dist = 0.0f;
+            unsigned long long my_bits = 0, my_em = 0;   // units of 2^-16
+            float my_dist = 0.0f;
             const int lend = min(L, lb + 32);
             // entropy-model bits (quantizer.py:226-228): one L2 sector per coordinate and lambda.  The loads of a lambda are
             // consumed (stored, summed) after the ranking of the NEXT lambda, which hides their latency.
@@ -220,13 +228,14 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_both_sweep_kernel(const QArgs
                         t_em += em_pend[u];
                     }
                 if (TOTALS) {
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) t_em += __shfl_xor_sync(0xffffffffu, t_em, o);
-                    if (lane == em_lam - lb) my_em = t_em;
+                    // entropy-model bits are -log2 of frequencies: the saturating conversion only matters for garbage tables
+                    const unsigned w_em = __reduce_add_sync(0xffffffffu, __float2uint_rn(fminf(t_em, 1024.0f) * 65536.0f));
+                    if (lane == em_lam - lb) my_em = w_em;
                 }
                 em_lam = -1;
             };
-            for (int lam = lb; lam < lend; ++lam) {
+            size_t o_lam = (size_t)lb * (size_t)a.lam_stride + off;   // this thread's first output element of lambda lam
+            for (int lam = lb; lam < lend; ++lam, o_lam += (size_t)a.lam_stride) {
                 const float *prow = sPenL + (lam * VBQ_GROUP + col) * kPenSlots;   // this channel's penalties
                 const unsigned lmask = sMask[lam];
                 const float4 *pl = reinterpret_cast<const float4 *>(prow);
@@ -270,8 +279,9 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_both_sweep_kernel(const QArgs
                     if (gap[u] > kKeyGuard && ((lmask >> n) & 1u)) {
                         const int fg = wi[u] + (int)((K[u] >> (kd - n - 1)) & 1u);
                         const int il = clamp_index(fg, n, N, false), ir = clamp_index(fg, n, N, true);
-                        const float dl = fabsf(sTc[entry_of(n, il) * VBQ_GROUP] - mu[u]);
-                        const float dr = fabsf(sTc[entry_of(n, ir) * VBQ_GROUP] - mu[u]);
+                        const int lvl = imad(n, 2 * kRowStrideBytes, pbi) + (kRowStrideBytes << n);   // entry_of(n, 0)
+                        const float dl = fabsf(lds_pure((unsigned)imad(il, kRowStrideBytes, lvl)) - mu[u]);
+                        const float dr = fabsf(lds_pure((unsigned)imad(ir, kRowStrideBytes, lvl)) - mu[u]);
                         wi[u] = il;
                         if (dr < dl) {
                             const float tf = dl * (u ? r2.y : r2.x);
@@ -291,18 +301,16 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_both_sweep_kernel(const QArgs
                 }
                 int t_level = 0, qv[U] = {0, 0};
                 float t_bits = 0.0f, t_dist = 0.0f;
-                const size_t lam_off = (size_t)lam * (size_t)a.lam_stride;
-                const float *len_row = a.len ? a.len + ((size_t)lam * a.pen_channels + (a.pen_channels == 1 ? 0 : cc)) * (N + 1) : nullptr;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const int n = wn[u], Pn = (1 << n) + wi[u];
                     if ((TOTALS || OUTS) && ok[u]) {
                         const float zh = lds_pure((unsigned)(imad(n, 2 * kRowStrideBytes, imad(Pn, kRowStrideBytes, pbi))));
-                        const float len = len_row ? __ldg(len_row + n) : (float)n;
+                        const float len = prow[12 + n];
                         const int q = ((2 * Pn + 1) << (N - n)) - (2 << N) - 1;
                         qv[u] = q;
                         if (OUTS) {
-                            const size_t o = lam_off + off + u * u_step;
+                            const size_t o = o_lam + u * u_step;
                             // streaming stores: the outputs of a sweep are many times the L2 and must not evict the
                             // entropy-model tables that every tile gathers from
                             if (a.zhat) __stcs(a.zhat + o, zh);
@@ -324,16 +332,22 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_both_sweep_kernel(const QArgs
                     for (int u = 0; u < U; ++u) em_pend[u] = ok[u] ? __ldg(a.em + ((size_t)lam * C + cc) * a.Q + qv[u]) : 0.0f;
                     em_lam = lam;
                 }
-                if (TOTALS) {   // the 64 float32 terms of the tile are added in float32, then accumulated as integers
+                if (TOTALS) {
+                    // code lengths: this thread's two terms in units of 2^-16, then an integer warp sum (one REDUX); the
+                    // distortion (unbounded) keeps the float32 butterfly over the 64 terms of the tile
                     t_level = __reduce_add_sync(0xffffffffu, t_level);
+                    unsigned long long w_bits;
+                    if (!big) w_bits = __reduce_add_sync(0xffffffffu, __float2uint_rn(t_bits * 65536.0f));
+                    else {   // absurdly long codes: float32 butterfly like the distortion
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        t_bits += __shfl_xor_sync(0xffffffffu, t_bits, o);
-                        t_dist += __shfl_xor_sync(0xffffffffu, t_dist, o);
+                        for (int o = 16; o > 0; o >>= 1) t_bits += __shfl_xor_sync(0xffffffffu, t_bits, o);
+                        w_bits = __float2ull_rn(t_bits * 65536.0f);
                     }
-                    if (lane == lam - lb) {   // the butterfly left the sums in every lane
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) t_dist += __shfl_xor_sync(0xffffffffu, t_dist, o);
+                    if (lane == lam - lb) {   // the sums are in every lane
                         my_level = t_level;
-                        my_bits = t_bits;
+                        my_bits = w_bits;
                         my_dist = t_dist;
                     }
                 }
@@ -342,8 +356,8 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_both_sweep_kernel(const QArgs
             if (TOTALS && lb + lane < L) {   // integers (units of 2^-16): the order of the tiles, which depends on the claims,
                 long long *w4 = wAcc + (size_t)(lb + lane) * kAccPerLambda;   // does not matter
                 w4[0] += my_level;
-                w4[1] += (long long)__float2ull_rn(my_bits * 65536.0f);
-                w4[2] += (long long)__float2ull_rn(my_em * 65536.0f);
+                w4[1] += (long long)my_bits;
+                w4[2] += (long long)my_em;
                 w4[3] += (long long)__float2ull_rn(my_dist * 65536.0f);   // 64-coordinate sums: exact to 2^-17
             }
             }
@@ -419,7 +433,7 @@ static int launch_both_sweep(QArgs a, int dev, int sms, cudaStream_t st) {
             b.totals = a.totals + (size_t)l0 * VBQ_TOTALS;
             b.partials = a.partials + (size_t)l0 * kMaxGrid * VBQ_TOTALS;
         }
-        // 768 bytes of penalties per lambda: the 8-byte accumulators behind the staging ring stay aligned
+        // 1536 bytes of penalties and code lengths per lambda: the 8-byte accumulators behind the staging ring stay aligned
         const size_t smem = fixed + per_lambda * b.n_lambda;
         VBQ_ENSURE_MAX_SMEM(kern, dev);
         CUDA_TRY(launch_pdl(kern, dim3((int)gx, 1), T, smem, st, b));
