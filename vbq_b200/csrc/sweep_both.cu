@@ -461,6 +461,7 @@ int vbq_launch_sweep_both(const QArgs &a, int dev, int sms, cudaStream_t st) {
     // into code lengths and entropy-model bits from shared-memory tables (0.69 + 0.45 ms).
     static const bool in_kernel = getenv("VBQ_EM_IN_KERNEL") != nullptr;
     if (em && a.em_bits && a.bits && !in_kernel && a.N == kSmemDepth && a.C % 4 == 0 && a.n_groups <= 2 * kMaxGrid &&
+        a.n_lambda <= 65535 &&   // the conditions of vbq_launch_em_gather
         (((uintptr_t)a.em_bits | (uintptr_t)a.em | (uintptr_t)a.bits) & 15) == 0) {
         QArgs b = a;
         b.em = nullptr;
