@@ -21,8 +21,10 @@ mu, sigma = bench.make_batch(prior, 3, dev)
 means = mu.cpu().numpy().reshape(bench.IMAGES, bench.H, bench.W, bench.C)
 logvars = (2 * torch.log(sigma)).cpu().numpy().reshape(means.shape)
 q.build_entropy_models_from_latents(means, logvars, lambs, add_n_smoothing=1)      # two-pass fit on the 24 images
-for i in range(3):
-    q.compress_latents(means[i:i + 1], logvars[i:i + 1], lambs)
+# The results are NumPy views of pinned buffers (no extra host copy); the caller keeps one result alive while the next call
+# runs, so the pinned allocator needs two generations of them: warm up the same way (cudaHostAlloc takes milliseconds).
+for i in range(8):
+    out = q.compress_latents(means[i:i + 1], logvars[i:i + 1], lambs)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 for i in range(bench.IMAGES):
