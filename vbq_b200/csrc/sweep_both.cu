@@ -19,7 +19,16 @@
 #include "bisect.cuh"
 
 constexpr int kPenSlots = 24;   // per (lambda, channel): penalties of depths 0..10 (three float4), then the code lengths of depths 0..10
-constexpr int kAccPerLambda = 4;   // sum n, sum code length, sum entropy-model bits, sum distortion
+constexpr int kAccPerLambda = 4;
+
+// 16 bytes from a 32-bit shared-memory address; not volatile: the penalty table does not change while a segment runs (the
+// caller makes the base address opaque once per segment, so that no load moves across the staging of the next segment)
+__device__ __forceinline__ float4 lds128_pure(unsigned addr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+   // sum n, sum code length, sum entropy-model bits, sum distortion
 
 // OUTS: per-coordinate outputs are requested (otherwise the call returns only the per-lambda totals); EM: entropy-model bits
 // (an output and / or column 2 of the totals)
@@ -87,6 +96,9 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_both_sweep_kernel(const QArgs
         // sMask[lam]: the same per lambda (the walk serves all lambdas and uses the union; the decision between the two ends
         // of a winning depth uses the lambda's own mask)
         const bool big = sBig != 0;
+        unsigned pen0 = (unsigned)__cvta_generic_to_shared(sPenL) + (unsigned)col * (kPenSlots * 4);   // this channel, lambda 0
+        unsigned mask0 = (unsigned)__cvta_generic_to_shared(sMask);
+        asm volatile("" : "+r"(pen0), "+r"(mask0));   // new values per segment as far as the compiler knows
         unsigned umask = 0;
         for (int lam = 0; lam < L; ++lam) {
             const float *pr = sPenL + (lam * VBQ_GROUP + col) * kPenSlots;
@@ -235,11 +247,10 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_both_sweep_kernel(const QArgs
                 em_lam = -1;
             };
             size_t o_lam = (size_t)lb * (size_t)a.lam_stride + off;   // this thread's first output element of lambda lam
-            for (int lam = lb; lam < lend; ++lam, o_lam += (size_t)a.lam_stride) {
-                const float *prow = sPenL + (lam * VBQ_GROUP + col) * kPenSlots;   // this channel's penalties
-                const unsigned lmask = sMask[lam];
-                const float4 *pl = reinterpret_cast<const float4 *>(prow);
-                const float4 pa = pl[0], pb = pl[1], pc = pl[2];
+            unsigned pen_a = pen0 + (unsigned)lb * (VBQ_GROUP * kPenSlots * 4);   // this channel's penalties, then code lengths
+            for (int lam = lb; lam < lend; ++lam, o_lam += (size_t)a.lam_stride, pen_a += VBQ_GROUP * kPenSlots * 4) {
+                const unsigned lmask = __float_as_uint(lds_pure(mask0 + 4u * (unsigned)lam));
+                const float4 pa = lds128_pure(pen_a), pb = lds128_pure(pen_a + 16), pc = lds128_pure(pen_a + 32);
                 const float pen[kSmemDepth + 1] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w, pc.x, pc.y, pc.z};
                 unsigned key[U][kSmemDepth + 1];
 #pragma unroll
@@ -285,7 +296,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_both_sweep_kernel(const QArgs
                         wi[u] = il;
                         if (dr < dl) {
                             const float tf = dl * (u ? r2.y : r2.x);
-                            const int dfar = (int)(__float_as_uint(__fmaf_rn(tf, tf, prow[n])) & kmask) - (int)(mkey[u] & kmask);
+                            const int dfar = (int)(__float_as_uint(__fmaf_rn(tf, tf, lds_pure(pen_a + 4u * (unsigned)n))) & kmask) - (int)(mkey[u] & kmask);
                             if (dfar > (int)kKeyGuard) wi[u] = ir;
                             else gap[u] = 0u;
                         }
@@ -294,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_both_sweep_kernel(const QArgs
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     if (gap[u] <= kKeyGuard) {   // not certified for this lambda: literal search
-                        const int r = reference_search(sTc, prow, 1, mu[u], sg[u], N);
+                        const int r = reference_search(sTc, sPenL + (lam * VBQ_GROUP + col) * kPenSlots, 1, mu[u], sg[u], N);
                         wn[u] = r >> 24;
                         wi[u] = r & 0xffffff;
                     }
@@ -306,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_both_sweep_kernel(const QArgs
                     const int n = wn[u], Pn = (1 << n) + wi[u];
                     if ((TOTALS || OUTS) && ok[u]) {
                         const float zh = lds_pure((unsigned)(imad(n, 2 * kRowStrideBytes, imad(Pn, kRowStrideBytes, pbi))));
-                        const float len = prow[12 + n];
+                        const float len = lds_pure(pen_a + 48u + 4u * (unsigned)n);
                         const int q = ((2 * Pn + 1) << (N - n)) - (2 << N) - 1;
                         qv[u] = q;
                         if (OUTS) {
