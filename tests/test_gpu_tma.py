@@ -153,6 +153,30 @@ def test_both_ends_sweep_small_depths_and_lambda_chunks(rows, C, N, L):
         assert torch.equal(tn, tn2) and _close(tn, tr, 2e-6), (outs, tn, tr)
 
 
+@pytest.mark.parametrize("lambs", [[0.5], [0.1, 0.5, 4.0]])
+def test_entropy_model_bits_with_and_without_totals(lambs):
+    """Every instantiation of em_gather_kernel in one process (with / without totals, after the single-lambda kernel and
+    after the sweep): each needs its own shared-memory attribute."""
+    N, rows, C = 10, 3000, 48
+    q, m, s = _case(rows, C, N, 5)
+    rng = np.random.default_rng(5)
+    L = len(lambs)
+    length = _lengths("fitted", rng, L, C, N)
+    pen = ops.with_host_copy(np.asarray(lambs, dtype=np.float32)[:, None, None] * length, m.device)
+    len_t = torch.from_numpy(length).to(m.device)
+    em = torch.from_numpy(rng.gamma(2.0, 3.0, size=(L, C, 2 ** (N + 1) - 1)).astype(np.float32)).to(m.device)
+    outs = ("zhat", "bits", "em_bits")
+    ref, _ = _run(q, m, s, pen, len_t, em, ops.FLAG_REFERENCE_WALK, outs, N)
+    for with_totals in (True, False, True, False):
+        if with_totals:
+            new, _ = _run(q, m, s, pen, len_t, em, 0, outs, N)
+        else:
+            new = {k: torch.full((L, rows, C), -7, dtype=DT[k], device=m.device) for k in outs}
+            ops.quantize_into(m, s, q.all_code_points, q._packed, pen, len_t, em, N, **new)
+            torch.cuda.synchronize()
+        assert _same(ref, new), with_totals
+
+
 @pytest.mark.parametrize("rows,C", [(300, 1024), (50000, 16), (129, 4080), (5, 2000)])
 def test_work_distribution_variants(rows, C):
     """More channel groups than tile queues (static row ranges, CTAs that span several groups), one group for all CTAs,

@@ -17,7 +17,10 @@ constexpr int kBothWarps = 17, kBothPairs = 2;   // measured (Kodak batch, one l
 constexpr int kGatherThreads = 1024;
 constexpr int kGatherStep = kGatherThreads / 4;   // rows per pass: a thread owns 4 channels of a row
 
-template <bool TOTALS>
+// LEN: the heap indices sit in the code-length planes, which receive the code lengths (after vbq_bisect_tma_kernel, whose two
+// TMA output boxes are taken); else they sit in the entropy-model planes themselves (after vbq_both_sweep_kernel, which writes
+// the code lengths itself): 8 instead of 12 bytes and 4 instead of 8 table look-ups per coordinate.
+template <bool TOTALS, bool LEN>
 __global__ void __launch_bounds__(kGatherThreads, 1) em_gather_kernel(const float *__restrict__ em, const float *__restrict__ len,
                                                                      int pen_channels, float *bits, float *em_bits,
                                                                      long long rows, int C, long long rows_per_cta,
@@ -42,7 +45,7 @@ __global__ void __launch_bounds__(kGatherThreads, 1) em_gather_kernel(const floa
             const int ch = i / Q, q1 = i - ch * Q + 1, t = __ffs(q1) - 1;
             sE[ch * Q + (1 << (N - t)) + (q1 >> (t + 1)) - 1] = __ldg(src + i);
         }
-        for (int k = threadIdx.x; k < (N + 1) * 128; k += kGatherThreads) {
+        for (int k = threadIdx.x; LEN && k < (N + 1) * 128; k += kGatherThreads) {
             const int c = min(g * VBQ_GROUP + 4 * (k & 3) + ((k >> 5) & 3), C - 1), n = k >> 7;
             sLen[k] = len ? __ldg(len + ((size_t)lam * pen_channels + (pen_channels == 1 ? 0 : c)) * (N + 1) + n) : (float)n;
         }
@@ -54,7 +57,7 @@ __global__ void __launch_bounds__(kGatherThreads, 1) em_gather_kernel(const floa
     float *pb = bits + (size_t)lam * lam_stride, *pe = em_bits + (size_t)lam * lam_stride;
     Acc128 acc = {0, 0};
     auto fetch = [&](int4 &q, const long long r) {
-        if (r < r1) q = __ldcs(reinterpret_cast<const int4 *>(pb + (size_t)r * C + c));
+        if (r < r1) q = __ldcs(reinterpret_cast<const int4 *>((LEN ? pb : pe) + (size_t)r * C + c));
     };
     auto emit = [&](const int4 q, const long long r) {
         if (r >= r1) return;
@@ -64,9 +67,9 @@ __global__ void __launch_bounds__(kGatherThreads, 1) em_gather_kernel(const floa
         for (int k = 0; k < 4; ++k) {
             const int K = min(max(qq[k], 1), Q);
             e[k] = sE[(col + k) * Q + K - 1];
-            b[k] = sLen[((31 - __clz(K)) * 4 + k) * 32 + lane];
+            if (LEN) b[k] = sLen[((31 - __clz(K)) * 4 + k) * 32 + lane];
         }
-        *reinterpret_cast<float4 *>(pb + (size_t)r * C + c) = make_float4(b[0], b[1], b[2], b[3]);
+        if (LEN) *reinterpret_cast<float4 *>(pb + (size_t)r * C + c) = make_float4(b[0], b[1], b[2], b[3]);
         *reinterpret_cast<float4 *>(pe + (size_t)r * C + c) = make_float4(e[0], e[1], e[2], e[3]);
         if (TOTALS) acc.add_q24((e[0] + e[1]) + (e[2] + e[3]));   // 4 terms per rounding, like the search kernel
     };
@@ -125,7 +128,29 @@ __global__ void __launch_bounds__(kGatherThreads, 1) em_gather_kernel(const floa
 }
 static_assert(kGatherThreads / 32 == 32, "one partial per lane of warp 0");
 
-static int launch_em_gather(const QArgs &a, int dev, int sms, cudaStream_t st) {
+// one function per kernel instantiation: VBQ_ENSURE_MAX_SMEM keeps a static "attribute set" flag per call site
+template <bool TOTALS, bool LEN>
+static int launch_em_gather_t(const QArgs &a, int dev, long long slices, long long rows_per_cta, size_t smem, cudaStream_t st) {
+    auto kern = em_gather_kernel<TOTALS, LEN>;
+    VBQ_ENSURE_MAX_SMEM(kern, dev);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)slices, (unsigned)a.n_groups, (unsigned)a.n_lambda);
+    cfg.blockDim = dim3(kGatherThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl = !getenv("VBQ_NO_PDL");
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a.em, a.len, a.pen_channels, a.bits, a.em_bits, a.rows, a.C, rows_per_cta, a.lam_stride,
+                                TOTALS ? a.totals : nullptr, TOTALS ? reinterpret_cast<Acc128 *>(a.partials) : nullptr,
+                                TOTALS ? a.ticket : nullptr));
+    return VBQ_OK;
+}
+
+static int launch_em_gather(const QArgs &a, int dev, int sms, cudaStream_t st, bool len_planes = true) {
     const size_t smem = ((size_t)VBQ_GROUP * a.Q + (size_t)(a.N + 1) * 128) * sizeof(float);
     // one CTA per SM (the table takes 131 KB): row slices such that the CTAs fill whole waves
     const long long per_slice = (long long)a.n_groups * a.n_lambda;
@@ -142,32 +167,18 @@ static int launch_em_gather(const QArgs &a, int dev, int sms, cudaStream_t st) {
         if (eff >= 0.93) break;
     }
     const long long rows_per_cta = (a.rows + slices - 1) / slices;
-    auto launch = [&](auto kern, double *tot, Acc128 *part, unsigned *tick) -> int {
-        VBQ_ENSURE_MAX_SMEM(kern, dev);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)slices, (unsigned)a.n_groups, (unsigned)a.n_lambda);
-        cfg.blockDim = dim3(kGatherThreads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        static const bool pdl = !getenv("VBQ_NO_PDL");
-        cfg.attrs = attr;
-        cfg.numAttrs = pdl ? 1 : 0;
-        CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, a.em, a.len, a.pen_channels, a.bits, a.em_bits, a.rows, a.C, rows_per_cta,
-                                    a.lam_stride, tot, part, tick));
-        return VBQ_OK;
-    };
-    if (a.totals) return launch(em_gather_kernel<true>, a.totals, reinterpret_cast<Acc128 *>(a.partials), a.ticket);
-    return launch(em_gather_kernel<false>, (double *)nullptr, (Acc128 *)nullptr, (unsigned *)nullptr);
+    if (len_planes)
+        return a.totals ? launch_em_gather_t<true, true>(a, dev, slices, rows_per_cta, smem, st)
+                        : launch_em_gather_t<false, true>(a, dev, slices, rows_per_cta, smem, st);
+    return a.totals ? launch_em_gather_t<true, false>(a, dev, slices, rows_per_cta, smem, st)
+                    : launch_em_gather_t<false, false>(a, dev, slices, rows_per_cta, smem, st);
 }
 
-// For vbq_both_sweep_kernel (sweep_both.cu), which leaves the winners' heap indices in the code-length planes of all lambdas
+// For vbq_both_sweep_kernel (sweep_both.cu), which leaves the winners' heap indices in the entropy-model planes of all lambdas
 int vbq_launch_em_gather(const QArgs &a, int dev, int sms, cudaStream_t st) {
-    if (a.N != kSmemDepth || !a.em || !a.em_bits || !a.bits || a.C % 4 != 0 || a.n_groups > 2 * kMaxGrid || a.n_lambda > 65535) return -1;
-    if ((((uintptr_t)a.em_bits | (uintptr_t)a.em | (uintptr_t)a.bits) & 15) != 0) return -1;
-    return launch_em_gather(a, dev, sms, st);
+    if (a.N != kSmemDepth || !a.em || !a.em_bits || a.C % 4 != 0 || a.n_groups > 2 * kMaxGrid || a.n_lambda > 65535) return -1;
+    if ((((uintptr_t)a.em_bits | (uintptr_t)a.em) & 15) != 0) return -1;
+    return launch_em_gather(a, dev, sms, st, false);
 }
 
 template <int EM, bool TOTALS, int OUT>

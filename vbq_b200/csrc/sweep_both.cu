@@ -327,7 +327,8 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_both_sweep_kernel(const QArgs
                             if (a.zhat) __stcs(a.zhat + o, zh);
                             if (a.qidx) __stcs(a.qidx + o, q);
                             if (a.level) __stcs(a.level + o, n);
-                            if (a.bits) __stcs(a.bits + o, a.kout ? __int_as_float(Pn) : len);
+                            if (a.bits) __stcs(a.bits + o, len);
+                            if (a.kout) __stcs(a.em_bits + o, __int_as_float(Pn));   // for em_gather_kernel
                         }
                         if (TOTALS) {
                             const float t = (zh - mu[u]) * (u ? r2.y : r2.x);
@@ -467,16 +468,15 @@ int vbq_launch_sweep_both(const QArgs &a, int dev, int sms, cudaStream_t st) {
     const bool outs = a.zhat || a.qidx || a.level || a.bits || a.em_bits;
     if (!tot && !outs) return VBQ_OK;   // nothing requested
     // Entropy-model bits as an OUTPUT: gathering them here costs an L2 sector per coordinate and lambda while the output
-    // stream of the sweep keeps evicting the tables (measured 1.64 ms for 16 lambdas on the Kodak batch); instead the code
-    // length plane carries the winner's heap index and em_gather_kernel (quantize_tma_both.cu) turns all lambda planes
-    // into code lengths and entropy-model bits from shared-memory tables (0.69 + 0.45 ms).
+    // stream of the sweep keeps evicting the tables (measured 1.64 ms for 16 lambdas on the Kodak batch); instead the
+    // entropy-model planes receive the winners' heap indices and em_gather_kernel (quantize_tma_both.cu) replaces them in all
+    // lambda planes by the table entries from shared memory.
     static const bool in_kernel = getenv("VBQ_EM_IN_KERNEL") != nullptr;
-    if (em && a.em_bits && a.bits && !in_kernel && a.N == kSmemDepth && a.C % 4 == 0 && a.n_groups <= 2 * kMaxGrid &&
+    if (em && a.em_bits && !in_kernel && a.N == kSmemDepth && a.C % 4 == 0 && a.n_groups <= 2 * kMaxGrid &&
         a.n_lambda <= 65535 &&   // the conditions of vbq_launch_em_gather
-        (((uintptr_t)a.em_bits | (uintptr_t)a.em | (uintptr_t)a.bits) & 15) == 0) {
+        (((uintptr_t)a.em_bits | (uintptr_t)a.em) & 15) == 0) {
         QArgs b = a;
-        b.em = nullptr;
-        b.em_bits = nullptr;
+        b.em = nullptr;   // no gather in the sweep kernel: the entropy-model planes receive the heap indices
         b.kout = 1;
         RETURN_IF(tot ? (launch_both_sweep<true, true, false, T>(b, dev, sms, st)) : (launch_both_sweep<false, true, false, T>(b, dev, sms, st)));
         return vbq_launch_em_gather(a, dev, sms, st);
