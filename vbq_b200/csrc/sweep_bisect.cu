@@ -123,6 +123,8 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_sweep_kernel(const QAr
         }
         __syncthreads();
         const float z0 = sTc[entry_of(0, 0) * VBQ_GROUP];
+        unsigned pen0 = (unsigned)__cvta_generic_to_shared(sPenL);
+        asm volatile("" : "+r"(pen0));   // opaque: the penalty loads below stay behind the barrier above
 
         while (q0 < n_tiles) {
             const int nxt = claim();
@@ -180,8 +182,8 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_bisect_sweep_kernel(const QAr
             float my_dist = 0.0f;
             const int lend = min(L, lb + 32);
             for (int lam = lb; lam < lend; ++lam) {
-                const float4 *pl = reinterpret_cast<const float4 *>(sPenL + lam * kPenSlots);
-                const float4 pa = pl[0], pb = pl[1], pc = pl[2];
+                const unsigned pen_a = pen0 + (unsigned)lam * (kPenSlots * 4);   // 32-bit shared-memory address: no generic-pointer arithmetic
+                const float4 pa = lds128_pure(pen_a), pb = lds128_pure(pen_a + 16), pc = lds128_pure(pen_a + 32);
                 const float pen[kSmemDepth + 1] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w, pc.x, pc.y, pc.z};
                 const unsigned guard = __float_as_uint(pc.w);
                 unsigned key[U][kSmemDepth + 1];

@@ -21,15 +21,6 @@
 constexpr int kPenSlots = 24;   // per (lambda, channel): penalties of depths 0..10 (three float4), then the code lengths of depths 0..10
 constexpr int kAccPerLambda = 4;
 
-// 16 bytes from a 32-bit shared-memory address; not volatile: the penalty table does not change while a segment runs (the
-// caller makes the base address opaque once per segment, so that no load moves across the staging of the next segment)
-__device__ __forceinline__ float4 lds128_pure(unsigned addr) {
-    float4 v;
-    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-   // sum n, sum code length, sum entropy-model bits, sum distortion
-
 // OUTS: per-coordinate outputs are requested (otherwise the call returns only the per-lambda totals); EM: entropy-model bits
 // (an output and / or column 2 of the totals)
 template <bool TOTALS, bool OUTS, bool EM, int kThreads>
