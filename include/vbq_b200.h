@@ -65,7 +65,7 @@ enum {
                                          on `stream` was enqueued (e.g. it synchronized after vbq_pack_code_points): the search
                                          kernel then fetches its code points while the stream's previous kernel still drains
                                          (programmatic dependent launch) instead of after it */
-#define VBQ_FLAG_NEIGHBOUR_EVERY_DEPTH 2048u /* arbitrary penalties (vbq_bisect_tma_kernel, both-ends variant): score the second
+#define VBQ_FLAG_NEIGHBOUR_EVERY_DEPTH 2048u /* arbitrary penalties (vbq_bisect_tma_kernel both-ends variant, vbq_both_sweep_kernel): score the second
                                           bracket end at every depth, not only where the penalties allow it to win (same
                                           results; diagnostics and tests) */
 #define VBQ_FLAG_NO_TMA 512u           /* single lambda: stage the latents with per-warp cp.async (vbq_bisect_kernel) instead
@@ -125,7 +125,11 @@ long long vbq_quantize_workspace_bytes(int n_lambda);
  *   d_bits      float32  d_length[lambda][c][n] (n if d_length is NULL)  (num_bits_dict[lamb])
  *   d_em_bits   float32  d_entropy_model[lambda][c][q]           (num_bits, quantizer.py:226-228)
  * d_totals (n_lambda, VBQ_TOTALS) float64 receives the per-lambda sums (deterministic reduction order).
- * d_length has the shape of d_penalty; d_entropy_model is (n_lambda, C, Q) float32. */
+ * d_length has the shape of d_penalty; d_entropy_model is (n_lambda, C, Q) float32.
+ * While the call runs, an entropy-model output plane may temporarily hold integer heap indices (em_gather_kernel replaces
+ * them before the call's work on the stream completes); code lengths above 512 bits and entropy-model entries above 512
+ * bits per coordinate are outside the exact range of the integer sums of the multi-lambda kernels (lengths fall back to a
+ * float32 sum, entropy-model sums saturate). */
 int vbq_quantize(const float *d_mu, const float *d_sigma, long long rows, int C,
                  const float *d_table, const float *d_packed, int N,
                  const float *d_penalty, const float *d_length, int n_lambda, int pen_channels,
