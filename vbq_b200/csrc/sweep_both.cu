@@ -9,11 +9,16 @@
 // candidate per depth in registers: the path node, or — at the depths where the penalties of some lambda and some channel
 // of the group dip below an earlier depth's (quantize_tma.cuh, iteration_both, explains why only there) — the nearer of the
 // path node and its in-level neighbour on the side of mu.  Every lambda then costs one packed add and one LOP3 per key, the
-// 3-input minimum chain and the VIADDMNMX gap chain with this thread's channel's penalties (a [Lambda][16][12] table in
-// shared memory).  Which end it is gets decided for the winning depth only, with the reference's own float32 scores of the
-// two ends (left end first on a tie).  A ranking that is not certified for some lambda is redone for that lambda by
-// `reference_search` (literal two-ended walk, IEEE float32).  max_bits_per_coord <= 10, C % 4 == 0, 16-byte aligned inputs,
-// finite non-negative penalties known on the host; other calls use one both-ends launch per lambda or vbq_sweep_kernel.
+// 3-input minimum chain and the VIADDMNMX gap chain with this thread's channel's penalties (a [Lambda][16][24] table of
+// penalties and code lengths in shared memory).  Which end it is gets decided for the winning depth only, and only where that
+// lambda's own mask says the neighbour can win: the left end unless the right end is strictly nearer AND the key of the left
+// end lies beyond the guard band (the left end comes first in the reference's candidate order, so the right end needs a
+// strictly better float32 score).  A ranking that is not certified for some lambda is redone for that lambda by
+// `reference_search` (literal two-ended walk, IEEE float32).  Entropy-model bits: summed in the kernel (loads consumed one
+// lambda later than issued) when only totals are wanted; as an output they are left to em_gather_kernel
+// (quantize_tma_both.cu) through the winner's heap index parked in the entropy-model plane.  max_bits_per_coord <= 10,
+// C % 4 == 0, 16-byte aligned inputs, finite non-negative penalties known on the host; other calls use one both-ends launch
+// per lambda or vbq_sweep_kernel.
 #include <stdlib.h>
 
 #include "bisect.cuh"
