@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_both_sweep_kernel(const QArgs
                     key[0][n] = (__float_as_uint(A.x) & kmask) | (unsigned)n;
                     key[1][n] = (__float_as_uint(A.y) & kmask) | (unsigned)n;
                 }
-                int wn[U], wi[U];   // winning depth, index of the winner within its level
+                int wn[U], wP[U];   // winning depth, heap index 2^n + i of the winner
                 unsigned mkey[U], gap[U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_both_sweep_kernel(const QArgs
                     gap[u] = min(g0, g1);
                     mkey[u] = m;
                     wn[u] = (int)(m & 15u);
-                    wi[u] = (int)(K[u] >> (kd - wn[u])) - (1 << wn[u]);
+                    wP[u] = (int)(K[u] >> (kd - wn[u]));
                 }
                 // The depth is certified if the gap exceeds the guard.  Where the neighbour can win, the two bracket ends of
                 // the winning depth (same penalty) are told apart by their distances: the left end comes first in the
@@ -284,18 +284,19 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_both_sweep_kernel(const QArgs
                 for (int u = 0; u < U; ++u) {
                     const int n = wn[u];
                     if (gap[u] > kKeyGuard && ((lmask >> n) & 1u)) {
-                        const int fg = wi[u] + (int)((K[u] >> (kd - n - 1)) & 1u);
+                        const int fg = wP[u] - (1 << n) + (int)((K[u] >> (kd - n - 1)) & 1u);
                         const int il = clamp_index(fg, n, N, false), ir = clamp_index(fg, n, N, true);
                         const int lvl = imad(n, 2 * kRowStrideBytes, pbi) + (kRowStrideBytes << n);   // entry_of(n, 0)
                         const float dl = fabsf(lds_pure((unsigned)imad(il, kRowStrideBytes, lvl)) - mu[u]);
                         const float dr = fabsf(lds_pure((unsigned)imad(ir, kRowStrideBytes, lvl)) - mu[u]);
-                        wi[u] = il;
+                        int iw = il;
                         if (dr < dl) {
                             const float tf = dl * (u ? r2.y : r2.x);
                             const int dfar = (int)(__float_as_uint(__fmaf_rn(tf, tf, lds_pure(pen_a + 4u * (unsigned)n))) & kmask) - (int)(mkey[u] & kmask);
-                            if (dfar > (int)kKeyGuard) wi[u] = ir;
+                            if (dfar > (int)kKeyGuard) iw = ir;
                             else gap[u] = 0u;
                         }
+                        wP[u] = (1 << n) + iw;
                     }
                 }
 #pragma unroll
@@ -303,14 +304,14 @@ __global__ void __launch_bounds__(kThreads, 1) vbq_both_sweep_kernel(const QArgs
                     if (gap[u] <= kKeyGuard) {   // not certified for this lambda: literal search
                         const int r = reference_search(sTc, sPenL + (lam * VBQ_GROUP + col) * kPenSlots, 1, mu[u], sg[u], N);
                         wn[u] = r >> 24;
-                        wi[u] = r & 0xffffff;
+                        wP[u] = (1 << wn[u]) + (r & 0xffffff);
                     }
                 }
                 int t_level = 0, qv[U] = {0, 0};
                 float t_bits = 0.0f, t_dist = 0.0f;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const int n = wn[u], Pn = (1 << n) + wi[u];
+                    const int n = wn[u], Pn = wP[u];
                     if ((TOTALS || OUTS) && ok[u]) {
                         const float zh = lds_pure((unsigned)(imad(n, 2 * kRowStrideBytes, imad(Pn, kRowStrideBytes, pbi))));
                         const float len = lds_pure(pen_a + 48u + 4u * (unsigned)n);
