@@ -176,6 +176,41 @@ static __device__ __forceinline__ int reference_search_warp(const float *sSc, co
     return wn << 24 | wi;
 }
 
+// The literal search for the coordinates of a unit that the certificate rejected, out of line (both-ends kernel: four
+// unrolled inline copies cost 2 % of the step through registers and code size although they run for 5 coordinates in 10^5;
+// the raw kernel measured no difference and keeps them inline).  Everything travels by value; r[u] < 0 means "unchanged",
+// else depth << 24 | index within the level.  The whole warp serves one coordinate when they are few (lane j scores
+// candidate j), else every lane searches for itself.  pen: penalties, pen_off: this lane's channel's offset into them.
+template <int U>
+struct SlowIO {
+    int Kd[U];
+    unsigned gap[U];
+    int r[U];
+};
+template <int U>
+static __device__ __noinline__ SlowIO<U> slow_search(SlowIO<U> io, const float *sSingle, const float *pen, int pen_off,
+                                                     unsigned mine, unsigned sg_off_bytes, int N, int kd, int lane) {
+#pragma unroll 1
+    for (int u = 0; u < U; ++u) {
+        io.r[u] = -1;
+        const float m_ = lds_u32(mine + u * 128), s_ = lds_u32(mine + sg_off_bytes + u * 128);
+        unsigned todo = __ballot_sync(0xffffffffu, io.gap[u] <= kKeyGuard);
+        if (__popc(todo) <= 6) {
+            while (todo) {
+                const int L = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int r = reference_search_warp(sSingle + (L & (VBQ_GROUP - 1)), pen + __shfl_sync(0xffffffffu, pen_off, L),
+                                                    __shfl_sync(0xffffffffu, m_, L), __shfl_sync(0xffffffffu, s_, L), N,
+                                                    __shfl_sync(0xffffffffu, io.Kd[u], L), kd, lane);
+                if (lane == L) io.r[u] = r;
+            }
+        } else if (io.gap[u] <= kKeyGuard) {
+            io.r[u] = reference_search_walk(sSingle + (lane & (VBQ_GROUP - 1)), pen + pen_off, m_, s_, N);
+        }
+    }
+    return io;
+}
+
 // OUT: compiled output set (bit 0 zhat, 1 qidx, 2 level, 3 bits), at most two arrays, in ascending bit order.
 // NT > 0: max_bits_per_coord == NT at compile time; NT == 0: run time (<= kSmemDepth).
 // W = consumer warps (the CTA has W + 1 warps); P = coordinate pairs per thread: a warp iteration ("unit") covers
@@ -802,30 +837,21 @@ __global__ void __launch_bounds__(32 * (W + 1), 1)
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) gap_min = min(gap_min, gap[u]);
-            if (__any_sync(0xffffffffu, gap_min <= kKeyGuard)) {
+            if (__any_sync(0xffffffffu, gap_min <= kKeyGuard)) {   // rare: a few coordinates in 10^5
+                SlowIO<U> io;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const float m_ = lds_u32(mine + u * 128), s_ = lds_u32(mine + 4 * kSgOff + u * 128);
-                    unsigned todo = __ballot_sync(0xffffffffu, gap[u] <= kKeyGuard);
-                    if (__popc(todo) <= 6) {
-                        while (todo) {
-                            const int L = __ffs(todo) - 1;
-                            todo &= todo - 1;
-                            const int cL = __shfl_sync(0xffffffffu, chan, L);
-                            const int r = reference_search_warp(sSingle + (L & (VBQ_GROUP - 1)), a.pen + (size_t)(a.pen_channels == 1 ? 0 : cL) * (N + 1),
-                                                                __shfl_sync(0xffffffffu, m_, L), __shfl_sync(0xffffffffu, s_, L),
-                                                                N, __shfl_sync(0xffffffffu, Kd[u], L), kd, lane);
-                            if (lane == L) {
-                                wn[u] = r >> 24;
-                                wP[u] = (1 << wn[u]) + (r & 0xffffff);
-                            }
-                        }
-                    } else if (gap[u] <= kKeyGuard) {
-                        const int r = reference_search_walk(sSc, a.pen + (size_t)(a.pen_channels == 1 ? 0 : chan) * (N + 1), m_, s_, N);
-                        wn[u] = r >> 24;
-                        wP[u] = (1 << wn[u]) + (r & 0xffffff);
-                    }
+                    io.Kd[u] = Kd[u];
+                    io.gap[u] = gap[u];
+                    io.r[u] = -1;
                 }
+                io = slow_search<U>(io, sSingle, a.pen, (a.pen_channels == 1 ? 0 : chan) * (N + 1), mine, 4 * kSgOff, N, kd, lane);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (io.r[u] >= 0) {
+                        wn[u] = io.r[u] >> 24;
+                        wP[u] = (1 << wn[u]) + (io.r[u] & 0xffffff);
+                    }
             }
             float dsum = 0.0f, bsum = 0.0f, esum = 0.0f;
 #pragma unroll
