@@ -4,8 +4,10 @@
 // the entropy-model gather of compress_latents (quantizer.py:223-228) fused in.
 #include "quantize_tma.cuh"
 
-constexpr int kBothWarps = 17, kBothPairs = 2;   // measured (Kodak batch, one lambda, no entropy-model gather): 15x2 73, 17x2 71,
-                                                 // 19x2 80, 23x1 74 us
+// consumer warps x coordinate pairs per thread, measured on the Kodak batch, one lambda, no entropy-model output: with the
+// neighbour mask and the literal search out of line 17x2 53.8, 19x2 52.2, 23x1 55.1 us (both ends at every depth: 15x2 73,
+// 17x2 71, 19x2 80, 23x1 74 us)
+constexpr int kBothWarps = 19, kBothPairs = 2;
 
 // Entropy-model bits (quantizer.py:226-228: entropy_models[lamb] gathered at the sorted index of z_hat).  Gathering inside
 // the search kernel costs one 32-byte L2 sector per coordinate — 32 L1 wavefronts per warp load, 33 us per launch on the
